@@ -1,0 +1,438 @@
+// bf16 attention kernels for the two production shapes of the ST block (st_transformer.py:70-83):
+//   spatial : non-causal attention over the S = 256 (or 128) tokens of one frame, head_dim 64 / 32
+//   temporal: causal attention over the <= 16 frames of one spatial position, with an optional K/V cache
+// Both read the fused QKV projection output [rows, 3d] (column order (3, h, hd), attention.py:38)
+// without any physical (B T) S C <-> (B S) T C transpose: the sequence structure is expressed through
+// TMA box coordinates (spatial) or row strides (temporal).
+// Tiles are staged in 128B/64B-swizzled shared memory (TMA for the spatial kernel), QK^T and PV run on
+// the warp-level tensor-core path (mma.sync m16n8k16 bf16 -> f32), softmax statistics are fp32 with
+// quad shuffles.  Optional qk-LayerNorm (attention.py:42-47) is applied to the staged Q/K rows in place.
+#include "kernels.cuh"
+#include "tensormap.cuh"
+
+namespace gn {
+namespace {
+
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+// byte offset of 16-byte chunk `c` of row `r` in a tile whose rows are HD bf16 wide, swizzled the way TMA
+// SWIZZLE_128B (HD = 64) / SWIZZLE_64B (HD = 32) lays it out (tile base aligned to 1024 B).
+template <int HD>
+__device__ __forceinline__ uint32_t swz(int r, int c) {
+  if (HD == 64) return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
+  return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+}
+
+// In-place LayerNorm(head_dim) of `nrows` staged rows (shared affine, eps 1e-5), CH = HD/8 lanes per row.
+template <int HD>
+__device__ __forceinline__ void qk_layernorm_rows(uint8_t* tile, int nrows, int tid, int nthreads,
+                                                  const float* __restrict__ gamma, const float* __restrict__ beta) {
+  constexpr int CH = HD / 8;
+  const int sub = tid % CH;
+  // uniform trip count: the shuffles below are executed by every lane of the warp
+  for (int rb = 0; rb < nrows; rb += nthreads / CH) {
+    const int r = rb + tid / CH;
+    const bool act = r < nrows;
+    uint4* p = reinterpret_cast<uint4*>(tile + swz<HD>(act ? r : 0, sub));
+    uint4 raw = act ? *p : make_uint4(0, 0, 0, 0);
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h2[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i];
+#pragma unroll
+    for (int o = CH / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)HD;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float dl = v[i] - mean; sq += dl * dl; }
+#pragma unroll
+    for (int o = CH / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / (float)HD + 1e-5f);
+    uint4 outv;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&outv);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c0 = sub * 8 + 2 * i;
+      ow[i] = pack_bf16x2((v[2 * i] - mean) * rstd * gamma[c0] + beta[c0],
+                          (v[2 * i + 1] - mean) * rstd * gamma[c0 + 1] + beta[c0 + 1]);
+    }
+    if (act) *p = outv;
+  }
+}
+
+// =====================================================================================
+// spatial attention: grid (S/128, heads, frames), 8 warps x 16 query rows
+// =====================================================================================
+constexpr int SP_THREADS = 256;
+constexpr int SP_QROWS = 128;
+
+template <int HD>
+__global__ void __launch_bounds__(SP_THREADS, 2)
+spatial_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                    bf16* __restrict__ out, int S, int d, float scale_log2e, const float* __restrict__ gamma,
+                    const float* __restrict__ beta) {
+  constexpr int ROWB = HD * 2;  // bytes per staged row
+  constexpr int CH = HD / 8;    // 16-byte chunks per row
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + SP_QROWS * ROWB;
+  uint8_t* sV = sK + S * ROWB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + S * ROWB);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, f = blockIdx.z;
+  const int frame_row0 = f * S;
+  const int q_row0 = frame_row0 + qt * SP_QROWS;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bars[0], (SP_QROWS + S) * ROWB);
+    tma_load_2d(sQ, &tmQ, &bars[0], h * HD, q_row0);
+    tma_load_2d(sK, &tmKV, &bars[0], d + h * HD, frame_row0);
+    mbar_arrive_expect_tx(&bars[1], S * ROWB);
+    tma_load_2d(sV, &tmKV, &bars[1], 2 * d + h * HD, frame_row0);
+  }
+  mbar_wait(&bars[0], 0);
+  if (gamma != nullptr) {
+    qk_layernorm_rows<HD>(sQ, SP_QROWS, tid, SP_THREADS, gamma, beta);
+    qk_layernorm_rows<HD>(sK, S, tid, SP_THREADS, gamma, beta);
+    __syncthreads();
+  }
+
+  const uint32_t sQa = smem_u32(sQ), sKa = smem_u32(sK), sVa = smem_u32(sV);
+  const int mi = lane >> 3, l8 = lane & 7;
+  const int g = lane >> 2, t4 = lane & 3;
+
+  uint32_t qf[HD / 16][4];
+#pragma unroll
+  for (int kk = 0; kk < HD / 16; ++kk)
+    ldsm_x4(qf[kk], sQa + swz<HD>(warp * 16 + l8 + (mi & 1) * 8, 2 * kk + (mi >> 1)));
+
+  float o[HD / 8][4];
+#pragma unroll
+  for (int j = 0; j < HD / 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  const int nkb = S / 64;
+  for (int kb = 0; kb < nkb; ++kb) {
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) {
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        uint32_t b[4];
+        ldsm_x4(b, sKa + swz<HD>(kb * 64 + (2 * jp + (mi >> 1)) * 8 + l8, 2 * kk + (mi & 1)));
+        mma_16816(s[2 * jp], qf[kk], b[0], b[1]);
+        mma_16816(s[2 * jp + 1], qf[kk], b[2], b[3]);
+      }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float a0 = exp2f((m0 - mn0) * scale_log2e), a1 = exp2f((m1 - mn1) * scale_log2e);
+    m0 = mn0; m1 = mn1;
+    const float off0 = mn0 * scale_log2e, off1 = mn1 * scale_log2e;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = exp2f(fmaf(s[j][0], scale_log2e, -off0));
+      s[j][1] = exp2f(fmaf(s[j][1], scale_log2e, -off0));
+      s[j][2] = exp2f(fmaf(s[j][2], scale_log2e, -off1));
+      s[j][3] = exp2f(fmaf(s[j][3], scale_log2e, -off1));
+      rs0 += s[j][0] + s[j][1];
+      rs1 += s[j][2] + s[j][3];
+    }
+    l0 = l0 * a0 + rs0;
+    l1 = l1 * a1 + rs1;
+#pragma unroll
+    for (int j = 0; j < HD / 8; ++j) { o[j][0] *= a0; o[j][1] *= a0; o[j][2] *= a1; o[j][3] *= a1; }
+    if (kb == 0) mbar_wait(&bars[1], 0);
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) {
+      uint32_t a[4];
+      a[0] = pack_bf16x2(s[2 * k2][0], s[2 * k2][1]);
+      a[1] = pack_bf16x2(s[2 * k2][2], s[2 * k2][3]);
+      a[2] = pack_bf16x2(s[2 * k2 + 1][0], s[2 * k2 + 1][1]);
+      a[3] = pack_bf16x2(s[2 * k2 + 1][2], s[2 * k2 + 1][3]);
+#pragma unroll
+      for (int jp = 0; jp < HD / 16; ++jp) {
+        uint32_t b[4];
+        ldsm_x4_t(b, sVa + swz<HD>(kb * 64 + k2 * 16 + (mi & 1) * 8 + l8, 2 * jp + (mi >> 1)));
+        mma_16816(o[2 * jp], a, b[0], b[1]);
+        mma_16816(o[2 * jp + 1], a, b[2], b[3]);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+
+  // stage the warp's 16 x HD output in its own (now dead) Q rows, then 16-byte coalesced stores
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < HD / 8; ++j) {
+    *reinterpret_cast<uint32_t*>(sQ + swz<HD>(warp * 16 + g, j) + t4 * 4) = pack_bf16x2(o[j][0] * i0, o[j][1] * i0);
+    *reinterpret_cast<uint32_t*>(sQ + swz<HD>(warp * 16 + g + 8, j) + t4 * 4) = pack_bf16x2(o[j][2] * i1, o[j][3] * i1);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 16 * CH / 32; ++it) {
+    const int idx = it * 32 + lane;
+    const int r = idx / CH, c = idx % CH;
+    const uint4 v = *reinterpret_cast<const uint4*>(sQ + swz<HD>(warp * 16 + r, c));
+    *reinterpret_cast<uint4*>(out + (int64_t)(q_row0 + warp * 16 + r) * d + h * HD + c * 8) = v;
+  }
+}
+
+template <int HD>
+int launch_spatial_t(const AttnArgs& a, int n_frames, int S, cudaStream_t st) {
+  const int d = a.n_heads * a.head_dim;
+  const int64_t rows = (int64_t)n_frames * S;
+  CUtensorMap tmQ, tmKV;
+  const CUtensorMapSwizzle sw = HD == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  GN_PROPAGATE(make_tensor_map_2d(&tmQ, a.qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * d, rows, 3 * d, HD, SP_QROWS, sw));
+  GN_PROPAGATE(make_tensor_map_2d(&tmKV, a.qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * d, rows, 3 * d, HD, S, sw));
+  const int smem = (SP_QROWS + 2 * S) * HD * 2 + 64 + 1024;
+  auto kern = spatial_attn_kernel<HD>;
+  static int set = 0;
+  if (smem > set) {
+    GN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    set = smem;
+  }
+  dim3 grid(S / SP_QROWS, a.n_heads, n_frames);
+  kern<<<grid, SP_THREADS, smem, st>>>(tmQ, tmKV, static_cast<bf16*>(a.out), S, d, a.scale * 1.4426950408889634f,
+                                       a.qk_gamma, a.qk_beta);
+  GN_CUDA_CHECK(cudaGetLastError());
+  ++g_launch_count;
+  return GN_OK;
+}
+
+// =====================================================================================
+// temporal attention: one CTA per (clip, spatial position), one warp per head
+// =====================================================================================
+template <int HD>
+__global__ void __launch_bounds__(512)
+temporal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, bf16* __restrict__ kcache,
+                     bf16* __restrict__ vcache, int S, int T, int t0, int Tq, int d, float scale_log2e,
+                     const float* __restrict__ gamma, const float* __restrict__ beta) {
+  constexpr int ROWB = HD * 2;
+  constexpr int CH = HD / 8;
+  constexpr int TILEB = 16 * ROWB;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = warp;
+  const int b = blockIdx.x / S, sp = blockIdx.x % S;
+  uint8_t* sQ = smem + warp * 3 * TILEB;
+  uint8_t* sK = sQ + TILEB;
+  uint8_t* sV = sK + TILEB;
+  const int Tk = t0 + Tq;
+  const int64_t fresh0 = ((int64_t)b * Tq) * S + sp;     // fresh row of local frame tl: fresh0 + tl*S
+  const int64_t cache0 = ((int64_t)b * T) * S + sp;      // cache row of frame j: cache0 + j*S
+
+#pragma unroll
+  for (int it = 0; it < 16 * CH / 32; ++it) {
+    const int idx = it * 32 + lane;
+    const int r = idx / CH, c = idx % CH;
+    uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q;
+    if (r < Tq) q = *reinterpret_cast<const uint4*>(qkv + (fresh0 + (int64_t)r * S) * 3 * d + h * HD + c * 8);
+    if (r < Tk) {
+      if (r < t0) {
+        const int64_t cr = (cache0 + (int64_t)r * S) * d + h * HD + c * 8;
+        k = *reinterpret_cast<const uint4*>(kcache + cr);
+        v = *reinterpret_cast<const uint4*>(vcache + cr);
+      } else {
+        const int64_t fr = (fresh0 + (int64_t)(r - t0) * S) * 3 * d + h * HD + c * 8;
+        k = *reinterpret_cast<const uint4*>(qkv + fr + d);
+        v = *reinterpret_cast<const uint4*>(qkv + fr + 2 * d);
+        if (kcache != nullptr) {
+          const int64_t cr = (cache0 + (int64_t)r * S) * d + h * HD + c * 8;
+          *reinterpret_cast<uint4*>(kcache + cr) = k;
+          *reinterpret_cast<uint4*>(vcache + cr) = v;
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(sQ + swz<HD>(r, c)) = q;
+    *reinterpret_cast<uint4*>(sK + swz<HD>(r, c)) = k;
+    *reinterpret_cast<uint4*>(sV + swz<HD>(r, c)) = v;
+  }
+  __syncwarp();
+  if (gamma != nullptr) {
+    qk_layernorm_rows<HD>(sQ, Tq, lane, 32, gamma, beta);
+    qk_layernorm_rows<HD>(sK, Tk, lane, 32, gamma, beta);
+    __syncwarp();
+  }
+  const uint32_t sQa = smem_u32(sQ), sKa = smem_u32(sK), sVa = smem_u32(sV);
+  const int mi = lane >> 3, l8 = lane & 7;
+  const int g = lane >> 2, t4 = lane & 3;
+
+  float s[2][4];
+  s[0][0] = s[0][1] = s[0][2] = s[0][3] = 0.f;
+  s[1][0] = s[1][1] = s[1][2] = s[1][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < HD / 16; ++kk) {
+    uint32_t qf[4], kf[4];
+    ldsm_x4(qf, sQa + swz<HD>(l8 + (mi & 1) * 8, 2 * kk + (mi >> 1)));
+    ldsm_x4(kf, sKa + swz<HD>((mi >> 1) * 8 + l8, 2 * kk + (mi & 1)));
+    mma_16816(s[0], qf, kf[0], kf[1]);
+    mma_16816(s[1], qf, kf[2], kf[3]);
+  }
+  // causal mask: query row i (frame t0 + i) sees keys j <= t0 + i   (attention.py:51-55)
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int key = j * 8 + 2 * t4 + e;
+      if (key > t0 + g) s[j][e] = -INFINITY;
+      if (key > t0 + g + 8) s[j][2 + e] = -INFINITY;
+      mx0 = fmaxf(mx0, s[j][e]);
+      mx1 = fmaxf(mx1, s[j][2 + e]);
+    }
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      s[j][e] = exp2f((s[j][e] - mx0) * scale_log2e);
+      s[j][2 + e] = exp2f((s[j][2 + e] - mx1) * scale_log2e);
+      l0 += s[j][e];
+      l1 += s[j][2 + e];
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  uint32_t pa[4];
+  pa[0] = pack_bf16x2(s[0][0], s[0][1]);
+  pa[1] = pack_bf16x2(s[0][2], s[0][3]);
+  pa[2] = pack_bf16x2(s[1][0], s[1][1]);
+  pa[3] = pack_bf16x2(s[1][2], s[1][3]);
+  float o[HD / 8][4];
+#pragma unroll
+  for (int jp = 0; jp < HD / 16; ++jp) {
+    uint32_t vf[4];
+    ldsm_x4_t(vf, sVa + swz<HD>((mi & 1) * 8 + l8, 2 * jp + (mi >> 1)));
+    o[2 * jp][0] = o[2 * jp][1] = o[2 * jp][2] = o[2 * jp][3] = 0.f;
+    o[2 * jp + 1][0] = o[2 * jp + 1][1] = o[2 * jp + 1][2] = o[2 * jp + 1][3] = 0.f;
+    mma_16816(o[2 * jp], pa, vf[0], vf[1]);
+    mma_16816(o[2 * jp + 1], pa, vf[2], vf[3]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < HD / 8; ++j) {
+    *reinterpret_cast<uint32_t*>(sQ + swz<HD>(g, j) + t4 * 4) = pack_bf16x2(o[j][0] * i0, o[j][1] * i0);
+    *reinterpret_cast<uint32_t*>(sQ + swz<HD>(g + 8, j) + t4 * 4) = pack_bf16x2(o[j][2] * i1, o[j][3] * i1);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 16 * CH / 32; ++it) {
+    const int idx = it * 32 + lane;
+    const int r = idx / CH, c = idx % CH;
+    if (r < Tq) {
+      const uint4 v = *reinterpret_cast<const uint4*>(sQ + swz<HD>(r, c));
+      *reinterpret_cast<uint4*>(out + (fresh0 + (int64_t)r * S) * d + h * HD + c * 8) = v;
+    }
+  }
+}
+
+template <int HD>
+int launch_temporal_t(const AttnArgs& a, int B, int S, int T, int t0, int Tq, void* kcache, void* vcache,
+                      cudaStream_t st) {
+  const int d = a.n_heads * a.head_dim;
+  const int smem = a.n_heads * 3 * 16 * HD * 2 + 1024;
+  auto kern = temporal_attn_kernel<HD>;
+  static int set = 0;
+  if (smem > 48 * 1024 && smem > set) {
+    GN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    set = smem;
+  }
+  kern<<<B * S, a.n_heads * 32, smem, st>>>(static_cast<const bf16*>(a.qkv), static_cast<bf16*>(a.out),
+                                            static_cast<bf16*>(kcache), static_cast<bf16*>(vcache), S, T, t0, Tq, d,
+                                            a.scale * 1.4426950408889634f, a.qk_gamma, a.qk_beta);
+  GN_CUDA_CHECK(cudaGetLastError());
+  ++g_launch_count;
+  return GN_OK;
+}
+
+}  // namespace
+
+bool fast_spatial_supported(const AttnArgs& a, int S) {
+  return a.act_bf16 && (a.head_dim == 64 || a.head_dim == 32) && (S == 128 || S == 256);
+}
+int fast_spatial_attention(const AttnArgs& a, int n_frames, int S, cudaStream_t st) {
+  return a.head_dim == 64 ? launch_spatial_t<64>(a, n_frames, S, st) : launch_spatial_t<32>(a, n_frames, S, st);
+}
+bool fast_temporal_supported(const AttnArgs& a, int T) {
+  return a.act_bf16 && (a.head_dim == 64 || a.head_dim == 32) && T <= 16 && a.n_heads <= 16;
+}
+int fast_temporal_attention(const AttnArgs& a, int B, int S, int T, int t0, int Tq, void* kcache, void* vcache,
+                            cudaStream_t st) {
+  return a.head_dim == 64 ? launch_temporal_t<64>(a, B, S, T, t0, Tq, kcache, vcache, st)
+                          : launch_temporal_t<32>(a, B, S, T, t0, Tq, kcache, vcache, st);
+}
+
+int generic_temporal_attention(const AttnArgs& a, int B, int S, int T, int t0, int Tq, void* kcache, void* vcache,
+                               cudaStream_t st);
+
+int launch_spatial_attention(const AttnArgs& a, int n_frames, int S, int force_generic, cudaStream_t st) {
+  if (!force_generic && fast_spatial_supported(a, S)) return fast_spatial_attention(a, n_frames, S, st);
+  return launch_generic_attention(a, n_frames, S, 0, st);
+}
+int launch_temporal_attention(const AttnArgs& a, int B, int S, int T, int t0, int Tq, void* kcache, void* vcache,
+                              int force_generic, cudaStream_t st) {
+  GN_REQUIRE(t0 >= 0 && Tq >= 1 && t0 + Tq <= T, "temporal attention: bad frame range t0=%d Tq=%d T=%d", t0, Tq, T);
+  GN_REQUIRE(t0 == 0 || (kcache && vcache), "temporal attention with t0 > 0 needs the K/V caches");
+  if (!force_generic && fast_temporal_supported(a, T))
+    return fast_temporal_attention(a, B, S, T, t0, Tq, kcache, vcache, st);
+  return generic_temporal_attention(a, B, S, T, t0, Tq, kcache, vcache, st);
+}
+
+}  // namespace gn

@@ -1,0 +1,406 @@
+// See gemm.cuh.  sm_100a only.
+#include "gemm.cuh"
+#include "ptx.cuh"
+#include "tensormap.cuh"
+
+namespace gn {
+
+unsigned long long g_launch_count = 0;
+
+// =====================================================================================
+// tcgen05 path
+// =====================================================================================
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int TILE_K_BYTES = 128;            // one 128B swizzle atom along K per stage
+constexpr int A_TILE_BYTES = BLOCK_M * TILE_K_BYTES;
+constexpr int NUM_ACC_STAGES = 2;
+constexpr int EPI_COLS = 32;                 // accumulator columns handled per epilogue step
+constexpr int NUM_EPI_WARPS = 4;
+constexpr int GEMM_THREADS = 32 * (2 + NUM_EPI_WARPS);
+constexpr int SMEM_LIMIT = 232448;           // 227 KB opt-in dynamic shared memory per CTA
+
+template <int BLOCK_N, typename OutT, bool DUAL>
+struct GemmSmem {
+  static constexpr int B_TILE_BYTES = BLOCK_N * TILE_K_BYTES;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int OUT_STAGE_BYTES = 32 * EPI_COLS * (int)sizeof(OutT);          // per warp per buffer
+  static constexpr int OUT2_STAGE_BYTES = DUAL ? 32 * EPI_COLS * 2 : 0;
+  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * 2 * (OUT_STAGE_BYTES + OUT2_STAGE_BYTES);
+  static constexpr int BAR_BYTES = 1024;
+  static constexpr int ALIGN_SLACK = 1024;
+  static constexpr int RAW_STAGES = (SMEM_LIMIT - STAGING_BYTES - BAR_BYTES - ALIGN_SLACK) / STAGE_BYTES;
+  static constexpr int STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + ALIGN_SLACK;
+  static_assert(STAGES >= 3, "pipeline too shallow");
+};
+
+struct TcArgs {
+  int M, N, K;
+  const float* bias;
+  const float* resid;
+  int64_t ldr;
+  int round_tf32;
+};
+
+template <typename OutT>
+__device__ __forceinline__ void stage_row_chunk(uint8_t* buf, uint32_t lane, const float (&v)[EPI_COLS]);
+
+// fp32: 32 cols = 128 B per row, SWIZZLE_128B (16B chunk index ^= row & 7)
+template <>
+__device__ __forceinline__ void stage_row_chunk<float>(uint8_t* buf, uint32_t lane, const float (&v)[EPI_COLS]) {
+  uint8_t* row = buf + lane * 128;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 f = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    *reinterpret_cast<float4*>(row + ((j ^ (lane & 7)) << 4)) = f;
+  }
+}
+// bf16: 32 cols = 64 B per row, SWIZZLE_64B (16B chunk index ^= (row >> 1) & 3)
+template <>
+__device__ __forceinline__ void stage_row_chunk<bf16>(uint8_t* buf, uint32_t lane, const float (&v)[EPI_COLS]) {
+  uint8_t* row = buf + lane * 64;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 p;
+    p.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+    p.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+    p.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+    p.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+    *reinterpret_cast<uint4*>(row + ((j ^ ((lane >> 1) & 3)) << 4)) = p;
+  }
+}
+
+template <typename InT, int BLOCK_N, int EPI, typename OutT, bool DUAL>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+                    const TcArgs args) {
+  using SM = GemmSmem<BLOCK_N, OutT, DUAL>;
+  constexpr int STAGES = SM::STAGES;
+  constexpr int BLOCK_K = TILE_K_BYTES / (int)sizeof(InT);     // 64 (bf16) or 32 (tf32)
+  constexpr int TMEM_COLS = NUM_ACC_STAGES * BLOCK_N;          // 128 / 256 / 512
+  constexpr uint32_t IDESC =
+      umma_idesc(sizeof(InT) == 2 ? UMMA_FMT_BF16 : UMMA_FMT_TF32, BLOCK_M, BLOCK_N);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;                                            // STAGES x 16 KB
+  uint8_t* smem_b = smem + STAGES * A_TILE_BYTES;                    // STAGES x BLOCK_N*128
+  uint8_t* staging = smem + STAGES * SM::STAGE_BYTES;                // epilogue staging
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + SM::STAGING_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* acc_full = bars + 2 * STAGES;
+  uint64_t* acc_empty = acc_full + NUM_ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NUM_ACC_STAGES);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+
+  const int num_m = (args.M + BLOCK_M - 1) / BLOCK_M;
+  const int num_n = args.N / BLOCK_N;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (args.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+    if (DUAL) tma_prefetch_desc(&tmOut2);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < NUM_ACC_STAGES; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], NUM_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
+          tma_load_2d(smem_a + stage * A_TILE_BYTES, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d(smem_b + stage * SM::B_TILE_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * A_TILE_BYTES));
+          const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(smem_b + stage * SM::B_TILE_BYTES));
+#pragma unroll
+          for (int k = 0; k < TILE_K_BYTES / 32; ++k) {
+            // advance 32 B (= one UMMA_K slice) inside the swizzle atom: +2 in 16-byte units
+            if (sizeof(InT) == 2)
+              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+            else
+              umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);          // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full[as]);                // accumulator complete
+        if (++as == NUM_ACC_STAGES) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const uint32_t q = warp & 3;                   // TMEM lane quarter this warp may access
+    const uint32_t ew = warp - 2;                  // staging slot
+    uint8_t* st0 = staging + ew * 2 * SM::OUT_STAGE_BYTES;
+    uint8_t* st1 = staging + NUM_EPI_WARPS * 2 * SM::OUT_STAGE_BYTES + ew * 2 * SM::OUT2_STAGE_BYTES;
+    uint32_t as = 0, aphase = 0, buf = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int row0 = m_blk * BLOCK_M + q * 32;
+      const int row = row0 + lane;
+      mbar_wait(&acc_full[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / EPI_COLS; ++c) {
+        const int col0 = n_blk * BLOCK_N + c * EPI_COLS;
+        uint32_t r[EPI_COLS];
+        tmem_ld_32x32b_x32(tmem_base + ((q * 32u) << 16) + as * BLOCK_N + c * EPI_COLS, r);
+        tmem_ld_wait();
+        if (c == BLOCK_N / EPI_COLS - 1) {
+          // accumulator stage fully read into registers: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[as]);
+        }
+        float v[EPI_COLS];
+#pragma unroll
+        for (int j = 0; j < EPI_COLS; ++j) v[j] = __uint_as_float(r[j]);
+        if (args.bias != nullptr) {
+          const float4* bp = reinterpret_cast<const float4*>(args.bias + col0);
+#pragma unroll
+          for (int j = 0; j < EPI_COLS / 4; ++j) {
+            const float4 b = __ldg(bp + j);
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
+        }
+        if (EPI == EPI_GELU) {
+#pragma unroll
+          for (int j = 0; j < EPI_COLS; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if (sizeof(OutT) == 4 && EPI != EPI_RESID && args.round_tf32) {
+#pragma unroll
+          for (int j = 0; j < EPI_COLS; ++j) v[j] = tf32_rn(v[j]);
+        }
+        if (EPI == EPI_RESID) {
+          if (row < args.M) {
+            const float4* rp = reinterpret_cast<const float4*>(args.resid + (int64_t)row * args.ldr + col0);
+#pragma unroll
+            for (int j = 0; j < EPI_COLS / 4; ++j) {
+              const float4 b = rp[j];
+              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+          }
+        }
+        // staging buffer `buf` was last used two steps ago: allow at most one newer bulk group in flight
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        stage_row_chunk<OutT>(st0 + buf * SM::OUT_STAGE_BYTES, lane, v);
+        if (DUAL) stage_row_chunk<bf16>(st1 + buf * SM::OUT2_STAGE_BYTES, lane, v);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmOut, st0 + buf * SM::OUT_STAGE_BYTES, col0, row0);
+          if (DUAL) tma_store_2d(&tmOut2, st1 + buf * SM::OUT2_STAGE_BYTES, col0, row0);
+          tma_store_commit();
+        }
+        buf ^= 1;
+      }
+      if (++as == NUM_ACC_STAGES) { as = 0; aphase ^= 1; }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+template <typename InT, int BLOCK_N, int EPI, typename OutT, bool DUAL>
+int launch_tc(const LinearArgs& a, cudaStream_t stream) {
+  using SM = GemmSmem<BLOCK_N, OutT, DUAL>;
+  constexpr int BLOCK_K = TILE_K_BYTES / (int)sizeof(InT);
+  const CUtensorMapDataType in_dt = sizeof(InT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapDataType out_dt =
+      sizeof(OutT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUtensorMap tmA, tmB, tmO, tmO2;
+  GN_PROPAGATE(make_tensor_map_2d(&tmA, a.A, in_dt, sizeof(InT), a.K, a.M, a.lda, BLOCK_K, BLOCK_M,
+                                  CU_TENSOR_MAP_SWIZZLE_128B));
+  GN_PROPAGATE(make_tensor_map_2d(&tmB, a.W, in_dt, sizeof(InT), a.K, a.N, a.ldw, BLOCK_K, BLOCK_N,
+                                  CU_TENSOR_MAP_SWIZZLE_128B));
+  GN_PROPAGATE(make_tensor_map_2d(&tmO, a.out, out_dt, sizeof(OutT), a.N, a.M, a.ldo, EPI_COLS, 32,
+                                  sizeof(OutT) == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B));
+  if (DUAL) {
+    GN_PROPAGATE(make_tensor_map_2d(&tmO2, a.out2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.N, a.M, a.ldo2, EPI_COLS,
+                                    32, CU_TENSOR_MAP_SWIZZLE_64B));
+  } else {
+    tmO2 = tmO;
+  }
+  auto kern = gemm_tcgen05_kernel<InT, BLOCK_N, EPI, OutT, DUAL>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    attr_set = true;
+  }
+  const int num_tiles = ceil_div(a.M, BLOCK_M) * (a.N / BLOCK_N);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  static int cached_sms = 0;
+  if (!cached_sms) cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev);
+  sms = cached_sms > 0 ? cached_sms : 148;
+  const int grid = num_tiles < sms ? num_tiles : sms;
+  TcArgs t{a.M, a.N, a.K, a.bias, a.resid, a.ldr, a.round_out_tf32};
+  kern<<<grid, GEMM_THREADS, SM::TOTAL, stream>>>(tmA, tmB, tmO, tmO2, t);
+  GN_CUDA_CHECK(cudaGetLastError());
+  ++g_launch_count;
+  return GN_OK;
+}
+
+template <typename InT, int BLOCK_N>
+int dispatch_epi(const LinearArgs& a, cudaStream_t s) {
+  if (a.epi == EPI_STORE) {
+    return a.out_bf16 ? launch_tc<InT, BLOCK_N, EPI_STORE, bf16, false>(a, s)
+                      : launch_tc<InT, BLOCK_N, EPI_STORE, float, false>(a, s);
+  }
+  if (a.epi == EPI_GELU) {
+    return a.out_bf16 ? launch_tc<InT, BLOCK_N, EPI_GELU, bf16, false>(a, s)
+                      : launch_tc<InT, BLOCK_N, EPI_GELU, float, false>(a, s);
+  }
+  if (a.epi == EPI_RESID) {
+    if (a.out_bf16) { set_error("EPI_RESID writes the fp32 residual stream"); return GN_ERR_INVALID; }
+    return a.out2 ? launch_tc<InT, BLOCK_N, EPI_RESID, float, true>(a, s)
+                  : launch_tc<InT, BLOCK_N, EPI_RESID, float, false>(a, s);
+  }
+  set_error("unknown epilogue %d", a.epi);
+  return GN_ERR_INVALID;
+}
+
+template <typename InT>
+int dispatch_n(const LinearArgs& a, cudaStream_t s) {
+  // BLOCK_N = 256 keeps the smem operand traffic per MMA cycle under the 128 B/clk port limit; the
+  // residual epilogues (fp32 + optional bf16 copy staging) take 128 to keep a deep TMA ring.
+  if (a.N % 256 == 0 && a.epi != EPI_RESID) return dispatch_epi<InT, 256>(a, s);
+  if (a.N % 128 == 0) return dispatch_epi<InT, 128>(a, s);
+  return dispatch_epi<InT, 64>(a, s);
+}
+
+// =====================================================================================
+// CUDA-core fp32 path (generic shapes, "exact" mode)
+// =====================================================================================
+constexpr int ST = 64, SK = 16;
+
+template <typename InT, typename OutT>
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const InT* __restrict__ A, int64_t lda, const InT* __restrict__ W, int64_t ldw,
+                 const float* __restrict__ bias, const float* __restrict__ resid, int64_t ldr, OutT* __restrict__ out,
+                 int64_t ldo, bf16* __restrict__ out2, int64_t ldo2, int M, int N, int K, int epi) {
+  __shared__ float sa[SK][ST + 1];
+  __shared__ float sw[SK][ST + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * ST, n0 = blockIdx.x * ST;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += SK) {
+    for (int i = threadIdx.x; i < ST * SK; i += 256) {
+      const int r = i / SK, c = i % SK;
+      const int gm = m0 + r, gn = n0 + r, gk = k0 + c;
+      sa[c][r] = (gm < M && gk < K) ? to_f32<InT>(A[(int64_t)gm * lda + gk]) : 0.f;
+      sw[c][r] = (gn < N && gk < K) ? to_f32<InT>(W[(int64_t)gn * ldw + gk]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SK; ++k) {
+      float av[4], wv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { av[i] = sa[k][ty * 4 + i]; wv[i] = sw[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (bias) v += bias[gn];
+      if (epi == EPI_GELU) v = gelu_erf(v);
+      if (epi == EPI_RESID) v += resid[(int64_t)gm * ldr + gn];
+      out[(int64_t)gm * ldo + gn] = from_f32<OutT>(v);
+      if (out2) out2[(int64_t)gm * ldo2 + gn] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+template <typename InT, typename OutT>
+int launch_simt(const LinearArgs& a, cudaStream_t s) {
+  dim3 grid(ceil_div(a.N, ST), ceil_div(a.M, ST));
+  gemm_simt_kernel<InT, OutT><<<grid, 256, 0, s>>>(
+      static_cast<const InT*>(a.A), a.lda, static_cast<const InT*>(a.W), a.ldw, a.bias, a.resid, a.ldr,
+      static_cast<OutT*>(a.out), a.ldo, static_cast<bf16*>(a.out2), a.ldo2, a.M, a.N, a.K, a.epi);
+  GN_CUDA_CHECK(cudaGetLastError());
+  ++g_launch_count;
+  return GN_OK;
+}
+
+}  // namespace
+
+int linear_forward(const LinearArgs& a, cudaStream_t stream) {
+  GN_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "linear_forward: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
+  GN_REQUIRE(a.A && a.W && a.out, "linear_forward: null operand");
+  GN_REQUIRE(a.epi != EPI_RESID || a.resid, "linear_forward: EPI_RESID needs a residual pointer");
+  const int esz = a.in_bf16 ? 2 : 4;
+  const bool tc_ok = !a.force_simt && (a.N % 64 == 0) && (a.K * esz % 16 == 0) && (a.lda * esz % 16 == 0) &&
+                     (a.ldw * esz % 16 == 0) && (a.ldo * (a.out_bf16 ? 2 : 4) % 16 == 0) &&
+                     (!a.out2 || a.ldo2 * 2 % 16 == 0) && (!a.resid || a.ldr % 4 == 0) &&
+                     (reinterpret_cast<uintptr_t>(a.A) % 16 == 0) && (reinterpret_cast<uintptr_t>(a.W) % 16 == 0) &&
+                     (reinterpret_cast<uintptr_t>(a.out) % 16 == 0) &&
+                     (!a.out2 || reinterpret_cast<uintptr_t>(a.out2) % 16 == 0) &&
+                     (!a.resid || reinterpret_cast<uintptr_t>(a.resid) % 16 == 0) &&
+                     (!a.bias || reinterpret_cast<uintptr_t>(a.bias) % 16 == 0) &&
+                     !(a.out2 && (a.epi != EPI_RESID || a.out_bf16));
+  if (tc_ok) return a.in_bf16 ? dispatch_n<bf16>(a, stream) : dispatch_n<float>(a, stream);
+  if (a.in_bf16)
+    return a.out_bf16 ? launch_simt<bf16, bf16>(a, stream) : launch_simt<bf16, float>(a, stream);
+  return a.out_bf16 ? launch_simt<float, bf16>(a, stream) : launch_simt<float, float>(a, stream);
+}
+
+}  // namespace gn

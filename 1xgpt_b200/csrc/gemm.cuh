@@ -1,0 +1,45 @@
+// Linear-layer GEMM  C[M,N] = epilogue(A[M,K] . W[N,K]^T)  for the ST-transformer
+// (QKV / proj / fc1 / fc2 / readout: reference genie/attention.py:27,32,38,60,
+//  genie/st_transformer.py:15-25, genie/st_mask_git.py:60-61,262).
+//
+// Two device paths, selected by SHAPE (not by backend):
+//   * gemm_tcgen05_kernel : persistent, warp-specialised sm_100a kernel.  TMA (128B-swizzled K-major
+//     tiles) -> smem ring -> tcgen05.mma (one issuing thread, fp32 accumulators double-buffered in
+//     TMEM) -> epilogue warps (tcgen05.ld, bias / erf-GELU / residual in registers) -> swizzled smem
+//     staging -> TMA store.
+//   * gemm_simt_kernel    : plain CUDA-core fp32 tile kernel for shapes the tensor path does not take
+//     (N % 64 != 0, K % 8 != 0, tiny test shapes) and for the fp32 "exact" precision mode.
+#pragma once
+#include "common.cuh"
+
+namespace gn {
+
+enum EpiKind : int { EPI_STORE = 0, EPI_GELU = 1, EPI_RESID = 2 };
+
+struct LinearArgs {
+  const void* A;      // [M, lda]  bf16 or f32
+  int64_t lda;
+  const void* W;      // [N, ldw]  same dtype as A
+  int64_t ldw;
+  const float* bias;  // [N] or nullptr
+  const float* resid; // [M, ldr] f32 (EPI_RESID) or nullptr
+  int64_t ldr;
+  void* out;          // [M, ldo]  bf16 or f32
+  int64_t ldo;
+  void* out2;         // optional second output, bf16 copy of `out` (only EPI_RESID with f32 out)
+  int64_t ldo2;
+  int M, N, K;
+  int epi;            // EpiKind
+  int in_bf16;        // 1: A/W bf16 (kind::f16), 0: f32 (kind::tf32 on the tensor path)
+  int out_bf16;       // 1: out is bf16, 0: f32
+  int force_simt;     // 1: CUDA-core fp32 path regardless of shape
+  int round_out_tf32; // 1: round the fp32 output to tf32 (it feeds a kind::tf32 GEMM next)
+};
+
+// Enqueue on `stream`.  Returns GN_OK or a negative code (message via last_error()).
+int linear_forward(const LinearArgs& a, cudaStream_t stream);
+
+// number of kernels launched by linear_forward so far (bench's gpu_launches accounting)
+extern unsigned long long g_launch_count;
+
+}  // namespace gn

@@ -1,0 +1,59 @@
+// Launcher declarations for every kernel of the hot path (all enqueue on the given stream and
+// return GN_OK / negative code).
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+namespace gn {
+
+// ---- elementwise.cu
+int launch_embed(const int32_t* ids, const float* E, const float* mask_embed, const float* pos, float* x, int B,
+                 int T, int S, int t0, int Tact, int d, int V, int NV, int mask_id, cudaStream_t st);
+int launch_prep(const float* x, void* out, int out_bf16, const float* gamma, const float* beta, int n_rows, int d,
+                float scale, int S, int Tact, int tsel, cudaStream_t st, int round_tf32 = 0);
+int launch_cast_bf16(const float* in, bf16* out, int64_t n, cudaStream_t st);
+int launch_round_tf32(const float* in, float* out, int64_t n, cudaStream_t st);
+int launch_logits_transpose(const float* rows, float* out, int B, int Tl, int S, int C, int Tout, int tslot0,
+                            cudaStream_t st);
+
+// ---- attention.cu
+struct AttnArgs {
+  const void* qkv;        // [n_seq * n_q_tok(+..), 3*d] fused projection output, column order (3, h, hd)
+  void* out;              // [rows, d]
+  int act_bf16;           // activation dtype of qkv/out: 1 bf16, 0 f32
+  int n_heads, head_dim;
+  float scale;
+  const float* qk_gamma;  // [hd] shared q/k LayerNorm affine (attention.py:34,43-44) or nullptr
+  const float* qk_beta;
+  int round_tf32;         // fp32 activations only: round the output to tf32 (feeds a kind::tf32 GEMM)
+};
+// spatial: sequences = frames; tokens of a sequence are S consecutive rows.  non-causal.
+int launch_spatial_attention(const AttnArgs& a, int n_frames, int S, int force_generic, cudaStream_t st);
+// temporal: sequences = (clip, spatial position); token (b, tl, s) is row (b*Tq + tl)*S + s of qkv (fresh
+// frames t0..t0+Tq-1).  Keys/values of frames < t0 come from kcache/vcache [B, T, S, d] (nullptr when t0 == 0);
+// fresh k/v are written back to the caches when they are non-null.  causal.
+int launch_temporal_attention(const AttnArgs& a, int B, int S, int T, int t0, int Tq, void* kcache, void* vcache,
+                              int force_generic, cudaStream_t st);
+// generic standalone attention over [n_seq, n_tok] (SelfAttention.forward contract, any small shape)
+int launch_generic_attention(const AttnArgs& a, int n_seq, int n_tok, int causal, cudaStream_t st);
+
+// ---- decode.cu
+// factored softmax / argmax / confidence of one frame's logits rows [R, NV*V]  (st_mask_git.py:171-190)
+int launch_sample(const float* logits, int R, int V, int NV, int32_t* samples, float* conf, cudaStream_t st);
+// cosine re-mask + scatter for one MaskGIT step (st_mask_git.py:192-223), one CTA per clip
+int launch_remask(int32_t* prompt_frame, int64_t clip_stride, const int32_t* samples, const float* conf_or_noise,
+                  uint8_t* unmasked, int32_t* samples_out, int B, int S, int n_mask, int last_step, int mask_id,
+                  cudaStream_t st);
+// factored cross-entropy + argmax accuracy over logits rows (eval_utils.py:72-77, st_mask_git.py:236-250)
+//   targets: int32 per row (unfactorized id); weight: optional uint8 per row (relevant mask)
+//   acc[0] += sum loss, acc[1] += rows counted, acc[2] += rows whose per-vocab argmax all match
+int launch_ce(const float* logits, const int32_t* targets, int64_t target_stride_b, int rows_per_b, int R, int V, int NV,
+              const uint8_t* weight, double* acc, cudaStream_t st);
+// acc[3] += #(a == b)
+int launch_count_equal(const int32_t* a, int64_t a_stride_b, const int32_t* b, int64_t b_stride_b, int rows_per_b, int R,
+                       double* acc, cudaStream_t st);
+// all(prompt[:, t_from:] == mask_id) -> flag (0 = ok); device-side replacement of st_mask_git.py:155
+int launch_check_masked(const int32_t* prompt, int B, int T, int S, int t_from, int mask_id, int* flag, cudaStream_t st);
+
+}  // namespace gn

@@ -1,0 +1,762 @@
+// Host-side orchestration of the GENIE forward / MaskGIT decode on one GPU + the C ABI
+// (include/genie_b200.h).  All device work is enqueued on the caller's stream; the only host
+// synchronisation points are the ones the header documents.
+#include "kernels.cuh"
+#include "../../include/genie_b200.h"
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+using namespace gn;
+
+namespace gn {
+int generic_temporal_attention(const AttnArgs& a, int B, int S, int T, int t0, int Tq, void* kcache, void* vcache,
+                               cudaStream_t st);
+int fast_spatial_attention(const AttnArgs& a, int n_frames, int S, cudaStream_t st);
+bool fast_spatial_supported(const AttnArgs& a, int S);
+int fast_temporal_attention(const AttnArgs& a, int B, int S, int T, int t0, int Tq, void* kcache, void* vcache,
+                            cudaStream_t st);
+bool fast_temporal_supported(const AttnArgs& a, int T);
+}  // namespace gn
+
+namespace {
+
+struct AttnW {
+  void* qkv_w = nullptr;
+  float* qkv_b = nullptr;
+  void* proj_w = nullptr;
+  float* proj_b = nullptr;
+  float* norm_g = nullptr;
+  float* norm_b = nullptr;
+};
+struct LayerW {
+  AttnW attn[2];  // 0 spatial, 1 temporal
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  void* fc1_w = nullptr;
+  float* fc1_b = nullptr;
+  void* fc2_w = nullptr;
+  float* fc2_b = nullptr;
+};
+
+}  // namespace
+
+struct gn_model {
+  gn_config cfg;
+  int device = 0;
+  int act_bf16 = 1;     // activation / weight-matrix dtype between kernels
+  int force_simt = 0;
+  int tf32 = 0;         // tcgen05 kind::tf32 parity mode: every GEMM operand is pre-rounded to tf32 (RN)
+  int hid = 0, C = 0;   // mlp hidden, readout width NV*V
+  std::vector<LayerW> layers;
+  float* pos = nullptr;         // [T,S,d]
+  float* mask_embed = nullptr;  // [d]
+  float* E = nullptr;           // [NV, V, d]
+  void* out_w = nullptr;        // [C, d]
+  float* out_b = nullptr;       // [C]
+  std::set<std::string> have;
+  std::vector<void*> owned;
+
+  // chunk workspace
+  int64_t ws_tokens = 0;
+  float* x = nullptr;     // [n, d] fp32 residual stream
+  void* a = nullptr;      // [n, d] act
+  void* big = nullptr;    // [n, max(3d, hid)] act (qkv / mlp hidden)
+  void* o = nullptr;      // [n, d] act
+  int64_t rows_cap = 0;
+  float* rows = nullptr;  // [rows_cap, C] fp32 logits rows
+
+  // temporal K/V cache [L][cache_B][T][S][d] act
+  int cache_B = 0;
+  void* kcache = nullptr;
+  void* vcache = nullptr;
+
+  // decode buffers for B clips
+  int dec_B = 0;
+  float* logits_frame = nullptr;   // [B*S, C]
+  int32_t* samples_tmp = nullptr;  // [B*S]
+  float* conf = nullptr;           // [B*S]
+  uint8_t* unmasked = nullptr;     // [B*S]
+  int32_t* prompt_scratch = nullptr;  // [B,T,S]
+  int32_t* samples_scratch = nullptr; // [B*S]
+  uint8_t* weight = nullptr;       // [B,T,S]
+  int* flag = nullptr;             // device int
+  float* noise_dev = nullptr;      // host-API staging
+  int64_t noise_cap = 0;
+  int32_t* tokens_dev = nullptr;
+  int64_t tokens_cap = 0;
+
+  double flops_executed = 0.0;
+
+  size_t esz() const { return act_bf16 ? 2 : 4; }
+};
+
+namespace {
+
+int dev_alloc(gn_model* m, void** p, size_t bytes) {
+  GN_CUDA_CHECK(cudaMalloc(p, bytes ? bytes : 16));
+  m->owned.push_back(*p);
+  return GN_OK;
+}
+void dev_free(gn_model* m, void* p) {
+  if (!p) return;
+  for (auto& q : m->owned)
+    if (q == p) { q = nullptr; break; }
+  cudaFree(p);
+}
+
+int ensure_workspace(gn_model* m, int64_t n) {
+  if (n <= m->ws_tokens) return GN_OK;
+  const int d = m->cfg.d_model;
+  const int64_t wide = std::max<int64_t>(3 * d, m->hid);
+  dev_free(m, m->x); dev_free(m, m->a); dev_free(m, m->big); dev_free(m, m->o);
+  m->ws_tokens = 0;
+  GN_PROPAGATE(dev_alloc(m, (void**)&m->x, (size_t)n * d * 4));
+  GN_PROPAGATE(dev_alloc(m, &m->a, (size_t)n * d * m->esz()));
+  GN_PROPAGATE(dev_alloc(m, &m->big, (size_t)n * wide * m->esz()));
+  GN_PROPAGATE(dev_alloc(m, &m->o, (size_t)n * d * m->esz()));
+  m->ws_tokens = n;
+  return GN_OK;
+}
+int ensure_rows(gn_model* m, int64_t r) {
+  if (r <= m->rows_cap) return GN_OK;
+  dev_free(m, m->rows);
+  m->rows_cap = 0;
+  GN_PROPAGATE(dev_alloc(m, (void**)&m->rows, (size_t)r * m->C * 4));
+  m->rows_cap = r;
+  return GN_OK;
+}
+int ensure_cache(gn_model* m, int B) {
+  if (B <= m->cache_B) return GN_OK;
+  dev_free(m, m->kcache); dev_free(m, m->vcache);
+  m->cache_B = 0;
+  const size_t bytes = (size_t)m->cfg.num_layers * B * m->cfg.T * m->cfg.S * m->cfg.d_model * m->esz();
+  GN_PROPAGATE(dev_alloc(m, &m->kcache, bytes));
+  GN_PROPAGATE(dev_alloc(m, &m->vcache, bytes));
+  m->cache_B = B;
+  return GN_OK;
+}
+int ensure_decode(gn_model* m, int B) {
+  if (B <= m->dec_B) return GN_OK;
+  const int S = m->cfg.S, T = m->cfg.T;
+  dev_free(m, m->logits_frame); dev_free(m, m->samples_tmp); dev_free(m, m->conf); dev_free(m, m->unmasked);
+  dev_free(m, m->prompt_scratch); dev_free(m, m->samples_scratch); dev_free(m, m->weight);
+  m->dec_B = 0;
+  GN_PROPAGATE(dev_alloc(m, (void**)&m->logits_frame, (size_t)B * S * m->C * 4));
+  GN_PROPAGATE(dev_alloc(m, (void**)&m->samples_tmp, (size_t)B * S * 4));
+  GN_PROPAGATE(dev_alloc(m, (void**)&m->conf, (size_t)B * S * 4));
+  GN_PROPAGATE(dev_alloc(m, (void**)&m->unmasked, (size_t)B * S));
+  GN_PROPAGATE(dev_alloc(m, (void**)&m->prompt_scratch, (size_t)B * T * S * 4));
+  GN_PROPAGATE(dev_alloc(m, (void**)&m->samples_scratch, (size_t)B * S * 4));
+  GN_PROPAGATE(dev_alloc(m, (void**)&m->weight, (size_t)B * T * S));
+  if (!m->flag) GN_PROPAGATE(dev_alloc(m, (void**)&m->flag, sizeof(int)));
+  m->dec_B = B;
+  return GN_OK;
+}
+
+int chunk_clips_for(const gn_model* m, int Tact) {
+  const int ct = m->cfg.chunk_tokens > 0 ? m->cfg.chunk_tokens : 16384;
+  int c = ct / (Tact * m->cfg.S);
+  return c < 1 ? 1 : c;
+}
+
+int linear(gn_model* m, const void* A, int64_t lda, const void* W, int K, const float* bias, const float* resid,
+           void* out, int64_t ldo, void* out2, int M, int N, int epi, int out_bf16, cudaStream_t st) {
+  LinearArgs la{};
+  la.A = A; la.lda = lda; la.W = W; la.ldw = K; la.bias = bias; la.resid = resid; la.ldr = N;
+  la.out = out; la.ldo = ldo; la.out2 = out2; la.ldo2 = N;
+  la.M = M; la.N = N; la.K = K; la.epi = epi; la.in_bf16 = m->act_bf16; la.out_bf16 = out_bf16;
+  la.force_simt = m->force_simt;
+  la.round_out_tf32 = (m->tf32 && epi == EPI_GELU) ? 1 : 0;
+  m->flops_executed += 2.0 * M * (double)N * K;
+  return linear_forward(la, st);
+}
+
+// Runs the L ST blocks on `n = nb*Tact*S` compact rows already present in m->x.
+// reference: genie/st_transformer.py:70-83 (STBlock.forward), :115-120.
+int run_layers(gn_model* m, int b0, int nb, int t0, int Tact, bool use_cache, cudaStream_t st) {
+  const gn_config& c = m->cfg;
+  const int d = c.d_model, S = c.S, T = c.T, H = c.num_heads, hd = d / H;
+  const int n = nb * Tact * S;
+  const int bf = m->act_bf16;
+  const float scale = c.use_mup ? 8.0f / hd : 1.0f / sqrtf((float)hd);
+  const int tf = m->tf32;
+  const bool cp = bf || tf;  // GEMM A operands need a converted copy of the fp32 stream (bf16 cast / tf32 rounding)
+  bool a_is_x = false;       // does m->a currently hold convert(x)?
+  for (int l = 0; l < c.num_layers; ++l) {
+    const LayerW& w = m->layers[l];
+    // ---------------- spatial attention: x += proj(attn(qkv(norm1(x))))
+    const void* ain;
+    if (!c.qk_norm) {
+      GN_PROPAGATE(launch_prep(m->x, m->a, bf, w.ln1_g, w.ln1_b, n, d, 1.f, S, Tact, -1, st, tf));
+      ain = m->a;
+    } else if (cp) {
+      if (!a_is_x) GN_PROPAGATE(launch_prep(m->x, m->a, bf, nullptr, nullptr, n, d, 1.f, S, Tact, -1, st, tf));
+      ain = m->a;
+    } else {
+      ain = m->x;
+    }
+    GN_PROPAGATE(linear(m, ain, d, w.attn[0].qkv_w, d, w.attn[0].qkv_b, nullptr, m->big, 3 * d, nullptr, n, 3 * d,
+                        EPI_STORE, bf, st));
+    AttnArgs aa{};
+    aa.qkv = m->big; aa.out = m->o; aa.act_bf16 = bf; aa.n_heads = H; aa.head_dim = hd; aa.scale = scale;
+    aa.qk_gamma = w.attn[0].norm_g; aa.qk_beta = w.attn[0].norm_b; aa.round_tf32 = tf;
+    GN_PROPAGATE(launch_spatial_attention(aa, nb * Tact, S, c.generic_attention || !bf, st));
+    m->flops_executed += 4.0 * S * (double)d * n;
+    // the temporal QKV GEMM reads the un-normalised stream: emit its bf16 copy from this epilogue
+    GN_PROPAGATE(linear(m, m->o, d, w.attn[0].proj_w, d, w.attn[0].proj_b, m->x, m->x, d, bf ? m->a : nullptr, n, d,
+                        EPI_RESID, 0, st));
+    if (tf) GN_PROPAGATE(launch_prep(m->x, m->a, 0, nullptr, nullptr, n, d, 1.f, S, Tact, -1, st, 1));
+    // ---------------- temporal attention (no LayerNorm in front: st_transformer.py:78)
+    GN_PROPAGATE(linear(m, cp ? m->a : (const void*)m->x, d, w.attn[1].qkv_w, d, w.attn[1].qkv_b, nullptr, m->big,
+                        3 * d, nullptr, n, 3 * d, EPI_STORE, bf, st));
+    aa.qk_gamma = w.attn[1].norm_g; aa.qk_beta = w.attn[1].norm_b;
+    void *kc = nullptr, *vc = nullptr;
+    if (use_cache) {
+      const size_t layer_stride = (size_t)m->cache_B * T * S * d * m->esz();
+      const size_t clip_off = (size_t)b0 * T * S * d * m->esz();
+      kc = (char*)m->kcache + l * layer_stride + clip_off;
+      vc = (char*)m->vcache + l * layer_stride + clip_off;
+    }
+    GN_PROPAGATE(launch_temporal_attention(aa, nb, S, T, t0, Tact, kc, vc, c.generic_attention || !bf, st));
+    m->flops_executed += 4.0 * (t0 + Tact) * (double)d * n;
+    const bool copy_t = bf && c.qk_norm;
+    GN_PROPAGATE(linear(m, m->o, d, w.attn[1].proj_w, d, w.attn[1].proj_b, m->x, m->x, d, copy_t ? m->a : nullptr, n,
+                        d, EPI_RESID, 0, st));
+    // ---------------- MLP: x += fc2(gelu(fc1(norm2(x))))
+    if (!c.qk_norm) {
+      GN_PROPAGATE(launch_prep(m->x, m->a, bf, w.ln2_g, w.ln2_b, n, d, 1.f, S, Tact, -1, st, tf));
+      ain = m->a;
+    } else if (cp) {
+      if (tf) GN_PROPAGATE(launch_prep(m->x, m->a, 0, nullptr, nullptr, n, d, 1.f, S, Tact, -1, st, 1));
+      ain = m->a;
+    } else {
+      ain = m->x;
+    }
+    GN_PROPAGATE(linear(m, ain, d, w.fc1_w, d, w.fc1_b, nullptr, m->big, m->hid, nullptr, n, m->hid, EPI_GELU, bf, st));
+    const bool copy_m = bf && c.qk_norm && (l + 1 < c.num_layers);
+    GN_PROPAGATE(linear(m, m->big, m->hid, w.fc2_w, m->hid, w.fc2_b, m->x, m->x, d, copy_m ? m->a : nullptr, n, d,
+                        EPI_RESID, 0, st));
+    a_is_x = copy_m;
+  }
+  return GN_OK;
+}
+
+// embed (+pos) clips [b0, b0+nb), frames [t0, t0+Tact) of ids [B,T,S] into m->x, then the L blocks.
+int forward_chunk(gn_model* m, const int32_t* ids, int b0, int nb, int t0, int Tact, bool use_cache, cudaStream_t st) {
+  const gn_config& c = m->cfg;
+  GN_PROPAGATE(ensure_workspace(m, (int64_t)nb * Tact * c.S));
+  GN_PROPAGATE(launch_embed(ids + (int64_t)b0 * c.T * c.S, m->E, m->mask_embed, m->pos, m->x, nb, c.T, c.S, t0, Tact,
+                            c.d_model, c.factored_vocab_size, c.num_factored_vocabs, c.image_vocab_size, st));
+  return run_layers(m, b0, nb, t0, Tact, use_cache, st);
+}
+
+// readout of rows (optionally only local frame `tsel`) of m->x into out_rows [R, C] fp32
+// reference: st_mask_git.py:262 (+ FixedMuReadout :316-323: input scaled by 256/d under muP)
+int readout(gn_model* m, int nb, int Tact, int tsel, float* out_rows, cudaStream_t st) {
+  const gn_config& c = m->cfg;
+  const int R = tsel >= 0 ? nb * c.S : nb * Tact * c.S;
+  const float mult = c.use_mup ? 256.0f / c.d_model : 1.0f;
+  const void* ain;
+  if (!m->act_bf16 && !m->tf32 && tsel < 0 && mult == 1.0f) {
+    ain = m->x;
+  } else {
+    GN_PROPAGATE(launch_prep(m->x, m->a, m->act_bf16, nullptr, nullptr, R, c.d_model, mult, c.S, Tact, tsel, st,
+                             m->tf32));
+    ain = m->a;
+  }
+  return linear(m, ain, c.d_model, m->out_w, c.d_model, m->out_b, nullptr, out_rows, m->C, nullptr, R, m->C, EPI_STORE,
+                0, st);
+}
+
+__global__ void fill_i32_kernel(int32_t* p, int64_t clip_stride, int64_t off, int64_t per_clip, int B, int32_t v) {
+  const int64_t total = (int64_t)B * per_clip;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    p[(i / per_clip) * clip_stride + off + (i % per_clip)] = v;
+  }
+}
+int fill_frames(int32_t* tokens, int B, int T, int S, int t_from, int32_t v, cudaStream_t st) {
+  if (t_from >= T) return GN_OK;
+  const int64_t per = (int64_t)(T - t_from) * S;
+  const int grid = (int)std::min<int64_t>(ceil_div64((int64_t)B * per, 256), 1184);
+  fill_i32_kernel<<<grid, 256, 0, st>>>(tokens, (int64_t)T * S, (int64_t)t_from * S, per, B, v);
+  GN_CUDA_CHECK(cudaGetLastError());
+  ++g_launch_count;
+  return GN_OK;
+}
+
+__global__ void relevant_weight_kernel(const int32_t* __restrict__ ids, uint8_t* __restrict__ w, int64_t total, int TS,
+                                       int S, int mask_id) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)((i % TS) / S);
+    w[i] = (t > 0 && ids[i] == mask_id) ? 1 : 0;
+  }
+}
+
+// One maskgit_generate call (st_mask_git.py:123-229).  `recompute_from`: first frame whose hidden state /
+// temporal K,V must be (re)computed at step 0 when the K/V cache is on (0 for a stand-alone call).
+// CE hooks: when `ce_targets` != nullptr the step-0 logits are scored against it (evaluate.py:177).
+int maskgit_impl(gn_model* m, int32_t* prompt, int B, int out_t, int steps, int unmask_mode, const float* noise,
+                 int32_t* samples, float* logits0, int logits0_Tout, int logits0_slot, int recompute_from,
+                 const int32_t* ce_targets, double* acc, cudaStream_t st) {
+  const gn_config& c = m->cfg;
+  const int S = c.S, T = c.T;
+  GN_PROPAGATE(ensure_decode(m, B));
+  const bool cache = c.kv_cache != 0;
+  if (cache) GN_PROPAGATE(ensure_cache(m, B));
+  GN_CUDA_CHECK(cudaMemsetAsync(m->unmasked, 0, (size_t)B * S, st));
+  for (int step = 0; step < steps; ++step) {
+    int t0 = 0, Tact = T;
+    if (cache) {
+      t0 = step == 0 ? recompute_from : out_t;
+      Tact = out_t + 1 - t0;
+    }
+    const int cc = chunk_clips_for(m, Tact);
+    for (int b0 = 0; b0 < B; b0 += cc) {
+      const int nb = std::min(cc, B - b0);
+      GN_PROPAGATE(forward_chunk(m, prompt, b0, nb, t0, Tact, cache, st));
+      GN_PROPAGATE(readout(m, nb, Tact, out_t - t0, m->logits_frame + (int64_t)b0 * S * m->C, st));
+    }
+    if (step == 0) {
+      if (logits0) GN_PROPAGATE(launch_logits_transpose(m->logits_frame, logits0, B, 1, S, m->C, logits0_Tout,
+                                                        logits0_slot, st));
+      if (ce_targets)
+        GN_PROPAGATE(launch_ce(m->logits_frame, ce_targets, (int64_t)T * S, S, B * S, c.factored_vocab_size,
+                               c.num_factored_vocabs, nullptr, acc, st));
+    }
+    GN_PROPAGATE(launch_sample(m->logits_frame, B * S, c.factored_vocab_size, c.num_factored_vocabs, m->samples_tmp,
+                               m->conf, st));
+    const bool last = step == steps - 1;
+    const int n_mask = last ? 0 : (int)std::ceil(std::cos((step + 1.0) / steps * M_PI / 2.0) * S);
+    const float* cf = nullptr;
+    if (!last) cf = unmask_mode == GN_UNMASK_GREEDY ? m->conf : noise + (int64_t)step * B * S;
+    GN_PROPAGATE(launch_remask(prompt + (int64_t)out_t * S, (int64_t)T * S, m->samples_tmp, cf, m->unmasked, samples, B,
+                               S, n_mask, last ? 1 : 0, c.image_vocab_size, st));
+  }
+  return GN_OK;
+}
+
+int check_generate_args(gn_model* m, int B, int steps, float temperature, int unmask_mode, const float* noise) {
+  GN_REQUIRE(m != nullptr, "null model handle");
+  GN_REQUIRE(B > 0, "batch must be positive (got %d)", B);
+  GN_REQUIRE(steps >= 1, "maskgit_steps must be >= 1 (got %d)", steps);
+  GN_REQUIRE(temperature <= 1e-8f, "temperature > 0 (Categorical sampling, st_mask_git.py:182-187) is not implemented");
+  GN_REQUIRE(unmask_mode == GN_UNMASK_RANDOM || unmask_mode == GN_UNMASK_GREEDY,
+             "Expected `unmask_mode` to be one of ['greedy', 'random'], got %d", unmask_mode);
+  GN_REQUIRE(steps == 1 || unmask_mode == GN_UNMASK_GREEDY || noise != nullptr,
+             "unmask_mode='random' with maskgit_steps > 1 needs the caller's noise tensor [steps-1, B, S]");
+  return gn_model_check_weights(m);
+}
+
+int sync_check_flag(gn_model* m, int out_t, cudaStream_t st) {
+  int h = 0;
+  GN_CUDA_CHECK(cudaMemcpyAsync(&h, m->flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GN_CUDA_CHECK(cudaStreamSynchronize(st));
+  GN_REQUIRE(h == 0, "when generating z%d, frames %d and later must be masked", out_t, out_t);
+  return GN_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+extern "C" {
+
+int gn_version(void) { return GN_ABI_VERSION; }
+const char* gn_last_error(void) { return gn::last_error(); }
+uint64_t gn_kernel_launches(void) { return gn::g_launch_count; }
+
+int gn_model_create(gn_model** out, const gn_config* cfg, int device) {
+  GN_REQUIRE(out && cfg, "gn_model_create: null argument");
+  *out = nullptr;
+  GN_REQUIRE(cfg->num_layers > 0 && cfg->num_heads > 0 && cfg->d_model > 0, "invalid model dims");
+  GN_REQUIRE(cfg->d_model % cfg->num_heads == 0, "d_model %% num_heads != 0");
+  GN_REQUIRE(cfg->d_model % 8 == 0, "d_model must be a multiple of 8");
+  GN_REQUIRE(cfg->T > 0 && cfg->S > 0, "invalid T/S");
+  {
+    int h = (int)std::lround(std::sqrt((double)cfg->S));
+    GN_REQUIRE(h * h == cfg->S, "Expected S to be square");
+  }
+  GN_REQUIRE(cfg->num_factored_vocabs >= 1 && cfg->factored_vocab_size >= 2, "invalid vocab factorisation");
+  {
+    int64_t p = 1;
+    for (int i = 0; i < cfg->num_factored_vocabs; ++i) p *= cfg->factored_vocab_size;
+    GN_REQUIRE(p == cfg->image_vocab_size, "factored_vocab_size ** num_factored_vocabs != image_vocab_size");
+  }
+  GN_REQUIRE(cfg->precision >= GN_PREC_BF16 && cfg->precision <= GN_PREC_FP32, "unknown precision %d", cfg->precision);
+  int ndev = 0;
+  GN_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+  GN_REQUIRE(device >= 0 && device < ndev, "device %d not available (%d visible)", device, ndev);
+  cudaDeviceProp prop;
+  GN_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  GN_REQUIRE(prop.major == 10, "libgenie_b200 is built for sm_100a only (device %d is sm_%d%d)", device, prop.major,
+             prop.minor);
+  gn_model* m = new (std::nothrow) gn_model();
+  GN_REQUIRE(m, "out of host memory");
+  m->cfg = *cfg;
+  m->device = device;
+  m->act_bf16 = cfg->precision == GN_PREC_BF16;
+  m->force_simt = cfg->precision == GN_PREC_FP32;
+  m->tf32 = cfg->precision == GN_PREC_TF32;
+  m->hid = (int)(cfg->d_model * cfg->mlp_ratio);
+  m->C = cfg->num_factored_vocabs * cfg->factored_vocab_size;
+  m->layers.resize(cfg->num_layers);
+  *out = m;
+  return GN_OK;
+}
+
+void gn_model_destroy(gn_model* m) {
+  if (!m) return;
+  DeviceGuard g(m->device);
+  for (void* p : m->owned)
+    if (p) cudaFree(p);
+  delete m;
+}
+
+int gn_model_set_weight(gn_model* m, const char* key, const float* src, const int64_t* shape, int ndim, void* stream) {
+  GN_REQUIRE(m && key && src && shape, "gn_model_set_weight: null argument");
+  DeviceGuard g(m->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const gn_config& c = m->cfg;
+  const int d = c.d_model, hd = d / c.num_heads;
+  int64_t numel = 1;
+  for (int i = 0; i < ndim; ++i) numel *= shape[i];
+  std::string k(key);
+
+  auto want = [&](int64_t n) -> int {
+    GN_REQUIRE(numel == n, "weight %s: expected %lld elements, got %lld", key, (long long)n, (long long)numel);
+    return GN_OK;
+  };
+  auto put_f32 = [&](float** dst, int64_t n) -> int {
+    GN_PROPAGATE(want(n));
+    if (!*dst) GN_PROPAGATE(dev_alloc(m, (void**)dst, (size_t)n * 4));
+    GN_CUDA_CHECK(cudaMemcpyAsync(*dst, src, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    m->have.insert(k);
+    return GN_OK;
+  };
+  auto put_mat = [&](void** dst, int64_t n) -> int {
+    GN_PROPAGATE(want(n));
+    if (!*dst) GN_PROPAGATE(dev_alloc(m, dst, (size_t)n * m->esz()));
+    if (m->act_bf16) GN_PROPAGATE(launch_cast_bf16(src, (bf16*)*dst, n, st));
+    else if (m->tf32) GN_PROPAGATE(launch_round_tf32(src, (float*)*dst, n, st));
+    else GN_CUDA_CHECK(cudaMemcpyAsync(*dst, src, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    m->have.insert(k);
+    return GN_OK;
+  };
+
+  if (k == "pos_embed_TSC") return put_f32(&m->pos, (int64_t)c.T * c.S * d);
+  if (k == "token_embed.mask_token_embed") return put_f32(&m->mask_embed, d);
+  if (k.rfind("token_embed.factored_embeds.", 0) == 0) {
+    int i = -1;
+    if (sscanf(key, "token_embed.factored_embeds.%d.weight", &i) != 1 || i < 0 || i >= c.num_factored_vocabs) {
+      set_error("unknown weight key %s", key);
+      return GN_ERR_INVALID;
+    }
+    const int64_t n = (int64_t)c.factored_vocab_size * d;
+    GN_PROPAGATE(want(n));
+    if (!m->E) GN_PROPAGATE(dev_alloc(m, (void**)&m->E, (size_t)c.num_factored_vocabs * n * 4));
+    GN_CUDA_CHECK(cudaMemcpyAsync(m->E + (int64_t)i * n, src, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    m->have.insert(k);
+    return GN_OK;
+  }
+  if (k == "out_x_proj.weight") return put_mat(&m->out_w, (int64_t)m->C * d);
+  if (k == "out_x_proj.bias") return put_f32(&m->out_b, m->C);
+  int l = -1;
+  char rest[128] = "";
+  if (sscanf(key, "decoder.layers.%d.%127s", &l, rest) == 2 && l >= 0 && l < c.num_layers) {
+    LayerW& w = m->layers[l];
+    std::string r(rest);
+    for (int which = 0; which < 2; ++which) {
+      const std::string p = which == 0 ? "spatial_attn." : "temporal_attn.";
+      if (r.rfind(p, 0) != 0) continue;
+      const std::string t = r.substr(p.size());
+      AttnW& a = w.attn[which];
+      if (t == "qkv.weight") return put_mat(&a.qkv_w, (int64_t)3 * d * d);
+      if (t == "qkv.bias") return put_f32(&a.qkv_b, 3 * d);
+      if (t == "proj.weight") return put_mat(&a.proj_w, (int64_t)d * d);
+      if (t == "proj.bias") return put_f32(&a.proj_b, d);
+      if (t == "norm.weight") return put_f32(&a.norm_g, hd);
+      if (t == "norm.bias") return put_f32(&a.norm_b, hd);
+    }
+    if (r == "norm1.weight") return put_f32(&w.ln1_g, d);
+    if (r == "norm1.bias") return put_f32(&w.ln1_b, d);
+    if (r == "norm2.weight") return put_f32(&w.ln2_g, d);
+    if (r == "norm2.bias") return put_f32(&w.ln2_b, d);
+    if (r == "mlp.fc1.weight") return put_mat(&w.fc1_w, (int64_t)m->hid * d);
+    if (r == "mlp.fc1.bias") return put_f32(&w.fc1_b, m->hid);
+    if (r == "mlp.fc2.weight") return put_mat(&w.fc2_w, (int64_t)d * m->hid);
+    if (r == "mlp.fc2.bias") return put_f32(&w.fc2_b, d);
+  }
+  set_error("unknown weight key %s", key);
+  return GN_ERR_INVALID;
+}
+
+int gn_model_check_weights(gn_model* m) {
+  GN_REQUIRE(m, "null model handle");
+  const gn_config& c = m->cfg;
+  std::vector<std::string> need = {"pos_embed_TSC", "token_embed.mask_token_embed", "out_x_proj.weight",
+                                   "out_x_proj.bias"};
+  for (int i = 0; i < c.num_factored_vocabs; ++i)
+    need.push_back("token_embed.factored_embeds." + std::to_string(i) + ".weight");
+  for (int l = 0; l < c.num_layers; ++l) {
+    const std::string p = "decoder.layers." + std::to_string(l) + ".";
+    for (const char* a : {"spatial_attn.", "temporal_attn."}) {
+      need.push_back(p + a + "qkv.weight");
+      need.push_back(p + a + "proj.weight");
+      if (c.qkv_bias) need.push_back(p + a + "qkv.bias");
+      if (c.proj_bias) need.push_back(p + a + "proj.bias");
+      if (c.qk_norm) { need.push_back(p + a + "norm.weight"); need.push_back(p + a + "norm.bias"); }
+    }
+    if (!c.qk_norm)
+      for (const char* nm : {"norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias"}) need.push_back(p + nm);
+    need.push_back(p + "mlp.fc1.weight");
+    need.push_back(p + "mlp.fc2.weight");
+    if (c.mlp_bias) { need.push_back(p + "mlp.fc1.bias"); need.push_back(p + "mlp.fc2.bias"); }
+  }
+  for (const auto& k : need) {
+    if (!m->have.count(k)) {
+      set_error("missing weight %s", k.c_str());
+      return GN_ERR_STATE;
+    }
+  }
+  return GN_OK;
+}
+
+int gn_decoder_forward(gn_model* m, const float* x, float* y, int B, void* stream) {
+  GN_REQUIRE(m && x && y && B > 0, "gn_decoder_forward: invalid argument");
+  GN_PROPAGATE(gn_model_check_weights(m));
+  DeviceGuard g(m->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const gn_config& c = m->cfg;
+  const int cc = chunk_clips_for(m, c.T);
+  const int64_t per_clip = (int64_t)c.T * c.S * c.d_model;
+  for (int b0 = 0; b0 < B; b0 += cc) {
+    const int nb = std::min(cc, B - b0);
+    GN_PROPAGATE(ensure_workspace(m, (int64_t)nb * c.T * c.S));
+    GN_CUDA_CHECK(cudaMemcpyAsync(m->x, x + b0 * per_clip, (size_t)nb * per_clip * 4, cudaMemcpyDeviceToDevice, st));
+    GN_PROPAGATE(run_layers(m, b0, nb, 0, c.T, false, st));
+    GN_CUDA_CHECK(cudaMemcpyAsync(y + b0 * per_clip, m->x, (size_t)nb * per_clip * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  return GN_OK;
+}
+
+int gn_attention_forward(gn_model* m, int layer, int which, const float* x, float* y, int n_seq, int n_tok, int causal,
+                         void* stream) {
+  GN_REQUIRE(m && x && y && n_seq > 0 && n_tok > 0, "gn_attention_forward: invalid argument");
+  GN_REQUIRE(layer >= 0 && layer < m->cfg.num_layers && (which == 0 || which == 1), "bad layer/which");
+  GN_PROPAGATE(gn_model_check_weights(m));
+  DeviceGuard g(m->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const gn_config& c = m->cfg;
+  const int d = c.d_model, hd = d / c.num_heads, n = n_seq * n_tok;
+  const int bf = m->act_bf16;
+  const AttnW& w = m->layers[layer].attn[which];
+  GN_PROPAGATE(ensure_workspace(m, n));
+  const void* ain = x;
+  if (bf || m->tf32) {
+    GN_PROPAGATE(launch_prep(x, m->a, bf, nullptr, nullptr, n, d, 1.f, 1, 1, -1, st, m->tf32));
+    ain = m->a;
+  }
+  GN_PROPAGATE(linear(m, ain, d, w.qkv_w, d, w.qkv_b, nullptr, m->big, 3 * d, nullptr, n, 3 * d, EPI_STORE, bf, st));
+  AttnArgs aa{};
+  aa.qkv = m->big; aa.out = m->o; aa.act_bf16 = bf; aa.n_heads = c.num_heads; aa.head_dim = hd;
+  aa.scale = c.use_mup ? 8.0f / hd : 1.0f / sqrtf((float)hd);
+  aa.qk_gamma = w.norm_g; aa.qk_beta = w.norm_b; aa.round_tf32 = m->tf32;
+  GN_PROPAGATE(launch_generic_attention(aa, n_seq, n_tok, causal, st));
+  return linear(m, m->o, d, w.proj_w, d, w.proj_b, nullptr, y, d, nullptr, n, d, EPI_STORE, 0, st);
+}
+
+int gn_compute_logits(gn_model* m, const int32_t* ids, int B, float* logits, void* stream) {
+  GN_REQUIRE(m && ids && logits && B > 0, "gn_compute_logits: invalid argument");
+  GN_PROPAGATE(gn_model_check_weights(m));
+  DeviceGuard g(m->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const gn_config& c = m->cfg;
+  const int cc = chunk_clips_for(m, c.T);
+  for (int b0 = 0; b0 < B; b0 += cc) {
+    const int nb = std::min(cc, B - b0);
+    GN_PROPAGATE(forward_chunk(m, ids, b0, nb, 0, c.T, false, st));
+    GN_PROPAGATE(ensure_rows(m, (int64_t)nb * c.T * c.S));
+    GN_PROPAGATE(readout(m, nb, c.T, -1, m->rows, st));
+    GN_PROPAGATE(launch_logits_transpose(m->rows, logits + (int64_t)b0 * m->C * c.T * c.S, nb, c.T, c.S, m->C, c.T, 0,
+                                         st));
+  }
+  return GN_OK;
+}
+
+int gn_maskgit_generate(gn_model* m, int32_t* prompt, int B, int out_t, int steps, float temperature, int unmask_mode,
+                        const float* noise, int32_t* samples, float* logits0, void* stream) {
+  GN_PROPAGATE(check_generate_args(m, B, steps, temperature, unmask_mode, noise));
+  GN_REQUIRE(prompt && samples, "gn_maskgit_generate: null buffer");
+  GN_REQUIRE(out_t > 0, "maskgit_generate requires out_t > 0");
+  GN_REQUIRE(out_t < m->cfg.T, "out_t %d out of range (T=%d)", out_t, m->cfg.T);
+  DeviceGuard g(m->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  GN_PROPAGATE(ensure_decode(m, B));
+  GN_CUDA_CHECK(cudaMemsetAsync(m->flag, 0, sizeof(int), st));
+  GN_PROPAGATE(launch_check_masked(prompt, B, m->cfg.T, m->cfg.S, out_t, m->cfg.image_vocab_size, m->flag, st));
+  // The reference asserts before doing any work (st_mask_git.py:155); we must not mutate the prompt if
+  // the precondition fails, so this one check is synchronous, like the reference's.
+  GN_PROPAGATE(sync_check_flag(m, out_t, st));
+  return maskgit_impl(m, prompt, B, out_t, steps, unmask_mode, noise, samples, logits0, 1, 0, 0, nullptr, nullptr, st);
+}
+
+int gn_generate(gn_model* m, int32_t* tokens, int B, int t_prompt, int steps, float temperature, int unmask_mode,
+                const float* noise, float* logits0, void* stream) {
+  GN_PROPAGATE(check_generate_args(m, B, steps, temperature, unmask_mode, noise));
+  GN_REQUIRE(tokens, "gn_generate: null buffer");
+  const gn_config& c = m->cfg;
+  GN_REQUIRE(t_prompt >= 1 && t_prompt <= c.T, "num_prompt_frames %d out of range [1, %d]", t_prompt, c.T);
+  DeviceGuard g(m->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  GN_PROPAGATE(ensure_decode(m, B));
+  GN_PROPAGATE(fill_frames(tokens, B, c.T, c.S, t_prompt, c.image_vocab_size, st));
+  const int Tnew = c.T - t_prompt;
+  for (int t = t_prompt; t < c.T; ++t) {
+    const float* nz = noise ? noise + (int64_t)(t - t_prompt) * (steps - 1) * B * c.S : nullptr;
+    const int from = (t == t_prompt) ? 0 : t - 1;
+    GN_PROPAGATE(maskgit_impl(m, tokens, B, t, steps, unmask_mode, nz, m->samples_scratch, logits0, Tnew, t - t_prompt,
+                              from, nullptr, nullptr, st));
+  }
+  return GN_OK;
+}
+
+int gn_generate_host(gn_model* m, int32_t* tokens_host, int B, int t_prompt, int steps, float temperature,
+                     int unmask_mode, const float* noise_host, void* stream) {
+  GN_REQUIRE(m && tokens_host && B > 0, "gn_generate_host: invalid argument");
+  DeviceGuard g(m->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const gn_config& c = m->cfg;
+  const int64_t ntok = (int64_t)B * c.T * c.S;
+  if (ntok > m->tokens_cap) {
+    dev_free(m, m->tokens_dev);
+    m->tokens_cap = 0;
+    GN_PROPAGATE(dev_alloc(m, (void**)&m->tokens_dev, (size_t)ntok * 4));
+    m->tokens_cap = ntok;
+  }
+  const int64_t nnoise = noise_host ? (int64_t)(c.T - t_prompt) * (steps - 1) * B * c.S : 0;
+  if (nnoise > m->noise_cap) {
+    dev_free(m, m->noise_dev);
+    m->noise_cap = 0;
+    GN_PROPAGATE(dev_alloc(m, (void**)&m->noise_dev, (size_t)nnoise * 4));
+    m->noise_cap = nnoise;
+  }
+  GN_CUDA_CHECK(cudaMemcpyAsync(m->tokens_dev, tokens_host, (size_t)ntok * 4, cudaMemcpyHostToDevice, st));
+  if (nnoise) GN_CUDA_CHECK(cudaMemcpyAsync(m->noise_dev, noise_host, (size_t)nnoise * 4, cudaMemcpyHostToDevice, st));
+  GN_PROPAGATE(gn_generate(m, m->tokens_dev, B, t_prompt, steps, temperature, unmask_mode, nnoise ? m->noise_dev : nullptr,
+                           nullptr, stream));
+  GN_CUDA_CHECK(cudaMemcpyAsync(tokens_host, m->tokens_dev, (size_t)ntok * 4, cudaMemcpyDeviceToHost, st));
+  GN_CUDA_CHECK(cudaStreamSynchronize(st));
+  return GN_OK;
+}
+
+int gn_teacher_forced_eval(gn_model* m, const int32_t* gt, int B, int steps, int unmask_mode, const float* noise,
+                           int32_t* samples_out, double* acc, void* stream) {
+  GN_PROPAGATE(check_generate_args(m, B, steps, 0.f, unmask_mode, noise));
+  GN_REQUIRE(gt && acc, "gn_teacher_forced_eval: null buffer");
+  DeviceGuard g(m->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const gn_config& c = m->cfg;
+  GN_PROPAGATE(ensure_decode(m, B));
+  const int64_t TS = (int64_t)c.T * c.S;
+  for (int t = 1; t < c.T; ++t) {
+    // inputs_masked = GT.clone(); inputs_masked[:, t:] = mask   (evaluate.py:109-110)
+    GN_CUDA_CHECK(cudaMemcpyAsync(m->prompt_scratch, gt, (size_t)B * TS * 4, cudaMemcpyDeviceToDevice, st));
+    GN_PROPAGATE(fill_frames(m->prompt_scratch, B, c.T, c.S, t, c.image_vocab_size, st));
+    const float* nz = noise ? noise + (int64_t)(t - 1) * (steps - 1) * B * c.S : nullptr;
+    int32_t* sout = m->samples_scratch;
+    GN_PROPAGATE(maskgit_impl(m, m->prompt_scratch, B, t, steps, unmask_mode, nz, sout, nullptr, 1, 0, t - 1,
+                              gt + (int64_t)t * c.S, acc, st));
+    GN_PROPAGATE(launch_count_equal(sout, c.S, gt + (int64_t)t * c.S, TS, c.S, B * c.S, acc, st));
+    if (samples_out) {
+      GN_CUDA_CHECK(cudaMemcpy2DAsync(samples_out + (int64_t)(t - 1) * c.S, (size_t)(c.T - 1) * c.S * 4, sout,
+                                      (size_t)c.S * 4, (size_t)c.S * 4, B, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  return GN_OK;
+}
+
+int gn_forward_loss(gn_model* m, const int32_t* input_ids, const int32_t* labels, int B, float* logits, double* acc,
+                    void* stream) {
+  GN_REQUIRE(m && input_ids && labels && acc && B > 0, "gn_forward_loss: invalid argument");
+  GN_PROPAGATE(gn_model_check_weights(m));
+  DeviceGuard g(m->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const gn_config& c = m->cfg;
+  GN_PROPAGATE(ensure_decode(m, B));
+  const int TS = c.T * c.S;
+  {
+    const int64_t total = (int64_t)B * TS;
+    const int grid = (int)std::min<int64_t>(ceil_div64(total, 256), 1184);
+    relevant_weight_kernel<<<grid, 256, 0, st>>>(input_ids, m->weight, total, TS, c.S, c.image_vocab_size);
+    GN_CUDA_CHECK(cudaGetLastError());
+    ++g_launch_count;
+  }
+  const int cc = chunk_clips_for(m, c.T);
+  for (int b0 = 0; b0 < B; b0 += cc) {
+    const int nb = std::min(cc, B - b0);
+    GN_PROPAGATE(forward_chunk(m, input_ids, b0, nb, 0, c.T, false, st));
+    GN_PROPAGATE(ensure_rows(m, (int64_t)nb * TS));
+    GN_PROPAGATE(readout(m, nb, c.T, -1, m->rows, st));
+    GN_PROPAGATE(launch_ce(m->rows, labels + (int64_t)b0 * TS, TS, TS, nb * TS, c.factored_vocab_size,
+                           c.num_factored_vocabs, m->weight + (int64_t)b0 * TS, acc, st));
+    if (logits)
+      GN_PROPAGATE(launch_logits_transpose(m->rows, logits + (int64_t)b0 * m->C * TS, nb, c.T, c.S, m->C, c.T, 0, st));
+  }
+  return GN_OK;
+}
+
+int gn_linear_forward(const void* a, const void* w, const float* bias, const float* resid, void* out, void* out2, int M,
+                      int N, int K, int epi, int in_bf16, int out_bf16, int force_simt, void* stream) {
+  LinearArgs la{};
+  la.A = a; la.lda = K; la.W = w; la.ldw = K; la.bias = bias; la.resid = resid; la.ldr = N;
+  la.out = out; la.ldo = N; la.out2 = out2; la.ldo2 = N;
+  la.M = M; la.N = N; la.K = K; la.epi = epi; la.in_bf16 = in_bf16; la.out_bf16 = out_bf16; la.force_simt = force_simt;
+  return linear_forward(la, (cudaStream_t)stream);
+}
+
+int gn_sample_tokens(const float* logits_rows, int R, int V, int NV, int32_t* samples, float* conf, void* stream) {
+  GN_REQUIRE(logits_rows && samples && conf && R > 0, "gn_sample_tokens: invalid argument");
+  return launch_sample(logits_rows, R, V, NV, samples, conf, (cudaStream_t)stream);
+}
+int gn_remask_step(int32_t* prompt_frame, int64_t clip_stride, const int32_t* samples, const float* conf_or_noise,
+                   uint8_t* unmasked, int32_t* samples_out, int B, int S, int n_mask, int last_step, int mask_id,
+                   void* stream) {
+  GN_REQUIRE(prompt_frame && samples && unmasked && samples_out && B > 0 && S > 0, "gn_remask_step: invalid argument");
+  return launch_remask(prompt_frame, clip_stride, samples, conf_or_noise, unmasked, samples_out, B, S, n_mask, last_step,
+                       mask_id, (cudaStream_t)stream);
+}
+int gn_cross_entropy(const float* logits_rows, const int32_t* targets, int R, int V, int NV, const uint8_t* weight,
+                     double* acc, void* stream) {
+  GN_REQUIRE(logits_rows && targets && acc && R > 0, "gn_cross_entropy: invalid argument");
+  return launch_ce(logits_rows, targets, 0, R, R, V, NV, weight, acc, (cudaStream_t)stream);
+}
+
+double gn_model_flops_per_clip_forward(gn_model* m) {
+  if (!m) return 0.0;
+  const gn_config& c = m->cfg;
+  const double d = c.d_model;
+  const double per_tok_layer = 32.0 * d * d + 4.0 * d * (c.S + c.T);
+  return (c.num_layers * per_tok_layer + 2.0 * d * m->C) * c.T * c.S;
+}
+double gn_model_flops_executed(gn_model* m) { return m ? m->flops_executed : 0.0; }
+void gn_model_reset_counters(gn_model* m) {
+  if (m) m->flops_executed = 0.0;
+}
+
+}  // extern "C"

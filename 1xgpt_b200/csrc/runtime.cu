@@ -1,0 +1,71 @@
+// Error plumbing + tensor-map encoding (host only).
+#include "common.cuh"
+#include "tensormap.cuh"
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace gn {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int encode(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int rank, const cuuint64_t* dims,
+                  const cuuint64_t* strides_bytes, const cuuint32_t* box, CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return GN_ERR_CUDA;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(out, dt, rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu,%llu,%llu] box [%u,%u,%u] base %p",
+              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, base);
+    return GN_ERR_CUDA;
+  }
+  return GN_OK;
+}
+
+int make_tensor_map_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int elem_bytes, int64_t inner,
+                       int64_t outer, int64_t ld, int box_inner, int box_outer, CUtensorMapSwizzle swz) {
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  return encode(out, base, dt, 2, dims, strides, box, swz);
+}
+
+int make_tensor_map_3d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int elem_bytes, int64_t d0,
+                       int64_t d1, int64_t d2, int64_t stride1, int64_t stride2, int box0, int box1, int box2,
+                       CUtensorMapSwizzle swz) {
+  cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t strides[2] = {(cuuint64_t)stride1 * elem_bytes, (cuuint64_t)stride2 * elem_bytes};
+  cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, (cuuint32_t)box2};
+  return encode(out, base, dt, 3, dims, strides, box, swz);
+}
+
+}  // namespace gn

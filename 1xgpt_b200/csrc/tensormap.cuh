@@ -1,0 +1,17 @@
+// Host-side CUtensorMap construction.  cuTensorMapEncodeTiled is resolved at run time through
+// cudaGetDriverEntryPoint, so the library does not link against libcuda.
+#pragma once
+#include "common.cuh"
+
+namespace gn {
+
+// 2-D row-major tensor: `inner` contiguous elements per row, `outer` rows, row pitch `ld` elements.
+int make_tensor_map_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int elem_bytes, int64_t inner,
+                       int64_t outer, int64_t ld, int box_inner, int box_outer, CUtensorMapSwizzle swz);
+
+// 3-D tensor (dims innermost first), strides in elements for dims 1 and 2.
+int make_tensor_map_3d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int elem_bytes, int64_t d0,
+                       int64_t d1, int64_t d2, int64_t stride1, int64_t stride2, int box0, int box1, int box2,
+                       CUtensorMapSwizzle swz);
+
+}  // namespace gn

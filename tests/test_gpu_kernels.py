@@ -1,0 +1,208 @@
+"""GPU parity of the individual kernels (called through the C ABI) against fp32 references."""
+import ctypes as C
+import importlib
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import O, rel_fro
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    g = importlib.import_module("1xgpt_b200")
+    return g._lib.load(), g._lib
+
+
+def P(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def run_linear(lib, M, N, K, epi, in_bf16, out_bf16, dual=False, bias=True, simt=False, seed=0):
+    L, _l = lib
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    b = torch.randn(N, device="cuda", generator=g) if bias else None
+    r = torch.randn(M, N, device="cuda", generator=g) if epi == 2 else None
+    if in_bf16:
+        a_in, w_in = a.bfloat16().contiguous(), w.bfloat16().contiguous()
+        a_ref, w_ref = a_in.float(), w_in.float()
+    else:
+        a_in, w_in = a, w
+        a_ref, w_ref = a, w
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    out2 = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16) if dual else None
+    _l.check(L.gn_linear_forward(P(a_in), P(w_in), P(b), P(r), P(out), P(out2), M, N, K, epi, int(in_bf16),
+                                 int(out_bf16), int(simt), None))
+    torch.cuda.synchronize()
+    ref = a_ref.double() @ w_ref.double().t()
+    if b is not None:
+        ref = ref + b.double()
+    if epi == 1:
+        ref = torch.nn.functional.gelu(ref)
+    if epi == 2:
+        ref = ref + r.double()
+    return out, out2, ref
+
+
+# (M, N, K): production shapes of d=512 / d=256 / d=1024 layers plus ragged M and small K
+TC_SHAPES = [(256, 1536, 512), (4096, 512, 512), (1000, 2048, 512), (384, 512, 2048), (128, 768, 256),
+             (300, 1024, 1024), (128, 64, 64), (130, 192, 64), (8192, 1024, 512), (256, 4096, 1024)]
+
+
+@pytest.mark.parametrize("M,N,K", TC_SHAPES)
+def test_linear_bf16_store(lib, M, N, K):
+    out, _, ref = run_linear(lib, M, N, K, epi=0, in_bf16=True, out_bf16=True)
+    assert torch.isfinite(out.float()).all()
+    assert rel_fro(out.float(), ref) < 4e-3          # bf16 output rounding (2^-9 per element)
+    out, _, ref = run_linear(lib, M, N, K, epi=0, in_bf16=True, out_bf16=False)
+    assert rel_fro(out, ref) < 2e-5                  # exact bf16 products, fp32 accumulation
+
+
+@pytest.mark.parametrize("M,N,K", TC_SHAPES[:6])
+def test_linear_bf16_gelu_and_residual(lib, M, N, K):
+    out, _, ref = run_linear(lib, M, N, K, epi=1, in_bf16=True, out_bf16=True)
+    assert rel_fro(out.float(), ref) < 4e-3
+    out, out2, ref = run_linear(lib, M, N, K, epi=2, in_bf16=True, out_bf16=False, dual=True)
+    assert rel_fro(out, ref) < 2e-5
+    assert torch.equal(out2, out.bfloat16())         # the bf16 copy is the rounding of the fp32 output
+    out, _, ref = run_linear(lib, M, N, K, epi=2, in_bf16=True, out_bf16=False, dual=False, bias=False)
+    assert rel_fro(out, ref) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K", TC_SHAPES[:6])
+def test_linear_tf32(lib, M, N, K):
+    for epi in (0, 1, 2):
+        out, _, ref = run_linear(lib, M, N, K, epi=epi, in_bf16=False, out_bf16=False)
+        assert rel_fro(out, ref) < 1e-3              # tf32 operands: 2^-11 relative per product
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 96, 32), (17, 32, 8), (128, 128, 64), (300, 1024, 1024)])
+def test_linear_simt_matches(lib, M, N, K):
+    for epi in (0, 1, 2):
+        out, out2, ref = run_linear(lib, M, N, K, epi=epi, in_bf16=False, out_bf16=False, simt=True, dual=(epi == 2))
+        assert rel_fro(out, ref) < 1e-6
+        out, _, ref = run_linear(lib, M, N, K, epi=epi, in_bf16=True, out_bf16=True, simt=True)
+        assert rel_fro(out.float(), ref) < 4e-3
+
+
+def test_linear_tensor_vs_simt_bitwise_close(lib):
+    # same bf16 inputs through both device paths: differences only from fp32 summation order
+    o1, _, _ = run_linear(lib, 512, 512, 512, epi=0, in_bf16=True, out_bf16=False, simt=False, seed=3)
+    o2, _, _ = run_linear(lib, 512, 512, 512, epi=0, in_bf16=True, out_bf16=False, simt=True, seed=3)
+    assert rel_fro(o1, o2) < 1e-6
+
+
+# ------------------------------------------------------------------------------------- decode kernels
+def test_sample_tokens_bit_exact(lib):
+    L, _l = lib
+    torch.manual_seed(0)
+    R, V, NV = 777, 512, 2
+    logits = (torch.randn(R, NV * V) * 3).cuda()
+    samples = torch.empty(R, dtype=torch.int32, device="cuda")
+    conf = torch.empty(R, dtype=torch.float32, device="cuda")
+    _l.check(L.gn_sample_tokens(P(logits), R, V, NV, P(samples), P(conf), None))
+    lc = logits.cpu().reshape(R, NV, V)
+    probs = torch.softmax(lc, dim=2)
+    ids = torch.zeros(R, dtype=torch.int64)
+    cf = torch.ones(R)
+    for i in reversed(range(NV)):
+        s = probs[:, i].argmax(dim=1)
+        ids = ids * V + s
+        cf = cf * probs[:, i].gather(1, s[:, None])[:, 0]
+    assert torch.equal(samples.cpu().long(), ids)                       # integer ids: bit exact
+    assert torch.allclose(conf.cpu(), cf, rtol=2e-5, atol=0)
+
+
+def test_sample_tokens_tie_breaks_low_index(lib):
+    L, _l = lib
+    logits = torch.zeros(4, 1024, device="cuda")
+    logits[1, 7] = logits[1, 300] = 2.0          # tie in vocab 0 -> 7
+    logits[2, 512 + 9] = logits[2, 512 + 8] = 1.0  # tie in vocab 1 -> 8
+    samples = torch.empty(4, dtype=torch.int32, device="cuda")
+    conf = torch.empty(4, dtype=torch.float32, device="cuda")
+    _l.check(L.gn_sample_tokens(P(logits), 4, 512, 2, P(samples), P(conf), None))
+    assert samples.cpu().tolist() == [0, 7, 8 * 512, 0]
+
+
+@pytest.mark.parametrize("S,steps", [(256, 2), (256, 8), (16, 3), (64, 5)])
+def test_remask_bit_exact_vs_oracle_schedule(lib, S, steps):
+    """Drive the remask kernel with the oracle's per-step samples/noise and compare every intermediate."""
+    L, _l = lib
+    B, mask_id = 5, 262144
+    g = torch.Generator().manual_seed(S + steps)
+    noise = O.tie_free_noise(steps, B, S, seed=S * 7 + steps)
+    frame = torch.full((B, S), mask_id, dtype=torch.int64)
+    unmasked = torch.zeros(B, S, dtype=torch.bool)
+    d_frame = frame.to(torch.int32).cuda()
+    d_unm = torch.zeros(B, S, dtype=torch.uint8, device="cuda")
+    for step in range(steps):
+        samples = torch.randint(0, mask_id, (B, S), generator=g)
+        # oracle (st_mask_git.py:192-223)
+        prev_unm, prev = unmasked.clone(), frame.clone()
+        sf = samples.clone()
+        last = step == steps - 1
+        n = 0
+        if not last:
+            n = O.cosine_schedule_n(step, steps, S)
+            c = noise[step].clone()
+            c[unmasked] = float("inf")
+            order = O.stable_argsort(c)
+            unmasked.scatter_(1, order[:, n:], True)
+            sf.scatter_(1, order[:, :n], mask_id)
+        sf[prev_unm] = prev[prev_unm]
+        frame = sf
+        # kernel
+        d_s = samples.to(torch.int32).cuda()
+        d_out = torch.empty(B, S, dtype=torch.int32, device="cuda")
+        nz = noise[step].cuda().contiguous() if not last else None
+        _l.check(L.gn_remask_step(P(d_frame), S, P(d_s), P(nz), P(d_unm), P(d_out), B, S, n, int(last), mask_id, None))
+        torch.cuda.synchronize()
+        assert torch.equal(d_out.cpu().long(), frame)
+        assert torch.equal(d_frame.cpu().long(), frame)
+        if not last:
+            assert torch.equal(d_unm.cpu().bool(), unmasked)
+    assert (frame != mask_id).all()
+
+
+def test_remask_stable_ties(lib):
+    L, _l = lib
+    B, S, mask_id = 1, 32, 99
+    conf = torch.zeros(B, S, device="cuda")             # all equal -> order = index
+    frame = torch.full((B, S), mask_id, dtype=torch.int32, device="cuda")
+    unm = torch.zeros(B, S, dtype=torch.uint8, device="cuda")
+    samples = torch.arange(S, dtype=torch.int32, device="cuda").reshape(B, S)
+    out = torch.empty_like(samples)
+    _l.check(L.gn_remask_step(P(frame), S, P(samples), P(conf), P(unm), P(out), B, S, 10, 0, mask_id, None))
+    exp = torch.arange(S)
+    exp[:10] = mask_id
+    assert out.cpu()[0].tolist() == exp.tolist()
+
+
+def test_cross_entropy_matches_torch(lib):
+    L, _l = lib
+    torch.manual_seed(1)
+    R, V, NV = 1000, 512, 2
+    logits = (torch.randn(R, NV * V) * 2).cuda()
+    tgt = torch.randint(0, V ** NV, (R,))
+    w = (torch.rand(R) < 0.6).to(torch.uint8)
+    tgt_d = tgt.to(torch.int32).cuda()          # keep device buffers alive across the (async) call
+    w_d = w.cuda()
+    for weight in (None, w):
+        acc = torch.zeros(4, dtype=torch.float64, device="cuda")
+        _l.check(L.gn_cross_entropy(P(logits), P(tgt_d), R, V, NV, P(w_d) if weight is not None else None, P(acc),
+                                    None))
+        lc = logits.cpu().reshape(R, NV, V).double()
+        f = O.factorize_token_ids(tgt, NV, V)
+        ce = sum(torch.nn.functional.cross_entropy(lc[:, i], f[:, i], reduction="none") for i in range(NV))
+        ok = torch.stack([lc[:, i].argmax(1) == f[:, i] for i in range(NV)]).all(0)
+        sel = torch.ones(R, dtype=torch.bool) if weight is None else weight.bool()
+        a = acc.cpu()
+        assert a[1].item() == sel.sum().item()
+        assert abs(a[0].item() - ce[sel].sum().item()) < 1e-3 * R
+        assert a[2].item() == ok[sel].sum().item()

@@ -1,0 +1,213 @@
+"""GPU parity of the whole path (through the nn.Module mirror -> C ABI) against the golden fixtures that
+the reference itself produced (tests/golden/*.npz) and against the CPU oracle run live.
+
+Tolerances (rel = Frobenius-relative error of logits):
+  fp32 mode  (CUDA-core FMA)          rel <= 2e-5, temperature-0 token ids bit-exact
+  tf32 mode  (tcgen05 kind::tf32)     rel <= 1e-3   (the north-star bar)
+  bf16 mode  (tcgen05 kind::f16)      rel <= 2e-2   (the reference's own bf16-vs-fp32 gap is 3e-3..1e-2,
+                                                     SURVEY.md section 7.3-1); argmax ids must agree wherever
+                                                     the oracle's top-2 margin exceeds twice the max abs error
+"""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import O, build_b200_model, golden_cfg, golden_sd, load_golden, rel_fro
+
+pytestmark = pytest.mark.gpu
+
+TINY = ["tiny_preln", "tiny_qknorm_mup", "tiny_qknorm"]
+TOL = {"fp32": 2e-5, "tf32": 1e-3, "bf16": 2e-2}
+
+
+@pytest.mark.parametrize("name", TINY)
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_tiny_logits_match_reference(name, precision):
+    z = load_golden(name)
+    kw, sd = golden_cfg(z), golden_sd(z)
+    m = build_b200_model(kw, sd, precision=precision)
+    logits = m.compute_logits(torch.from_numpy(z["prompt"]).cuda())
+    ref = torch.from_numpy(z["logits"])
+    assert logits.shape == ref.shape
+    err = rel_fro(logits, ref)
+    print(f"{name} {precision}: rel {err:.3e}")
+    assert err < TOL[precision]
+
+
+@pytest.mark.parametrize("name", TINY)
+def test_tiny_maskgit_tokens_bit_exact_fp32(name):
+    z = load_golden(name)
+    kw, sd = golden_cfg(z), golden_sd(z)
+    for kv in (False, True):
+        m = build_b200_model(kw, sd, precision="fp32", kv_cache=kv)
+        prompt = torch.from_numpy(z["prompt"]).cuda()
+        samples, fl = m.maskgit_generate(prompt, 2, maskgit_steps=3, temperature=0.0,
+                                         noise=torch.from_numpy(z["noise"]))
+        assert torch.equal(samples.cpu(), torch.from_numpy(z["samples"]))
+        assert torch.equal(prompt.cpu(), torch.from_numpy(z["prompt_after"]))     # in-place mutation contract
+        assert rel_fro(fl, torch.from_numpy(z["logits0"])) < TOL["fp32"]
+        # greedy (confidence-driven) unmasking
+        prompt = torch.from_numpy(z["prompt"]).cuda()
+        sg, _ = m.maskgit_generate(prompt, 2, maskgit_steps=3, temperature=0.0, unmask_mode="greedy")
+        assert torch.equal(sg.cpu(), torch.from_numpy(z["samples_greedy"]))
+
+
+@pytest.mark.parametrize("name", TINY)
+def test_tiny_forward_loss_acc_and_generate(name):
+    z = load_golden(name)
+    kw, sd = golden_cfg(z), golden_sd(z)
+    m = build_b200_model(kw, sd, precision="fp32")
+    out = m(torch.from_numpy(z["fwd_in"]).cuda(), torch.from_numpy(z["ids"]).reshape(2, -1).cuda())
+    assert abs(float(out.loss) - float(z["fwd_loss"])) < 1e-4
+    assert abs(float(out.acc) - float(z["fwd_acc"])) < 1e-7
+    ids = torch.from_numpy(z["ids"])
+    for kv in (False, True):
+        m = build_b200_model(kw, sd, precision="fp32", kv_cache=kv)
+        gen = m.generate(ids[:, :2].reshape(2, -1).cuda(), None, max_new_tokens=2 * kw["S"], maskgit_steps=2,
+                         temperature=0.0, noise=torch.from_numpy(z["gen_noise"]))
+        assert torch.equal(gen.cpu(), torch.from_numpy(z["gen_tokens"]))
+
+
+@pytest.mark.parametrize("name", TINY)
+def test_tiny_teacher_forced_eval_matches_oracle(name):
+    z = load_golden(name)
+    kw, sd = golden_cfg(z), golden_sd(z)
+    cfg = O.OracleConfig(**kw)
+    ids = torch.from_numpy(z["ids"])
+    B = ids.shape[0]
+    noise = torch.stack([O.tie_free_noise(2, B, cfg.S, seed=900 + t) for t in range(cfg.T - 1)])
+    loss, acc, samples = O.teacher_forced_metrics(sd, cfg, ids.reshape(B, -1), 2, noise)
+    for kv in (False, True):
+        m = build_b200_model(kw, sd, precision="fp32", kv_cache=kv)
+        a, s = m.teacher_forced_eval(ids.reshape(B, -1).cuda(), maskgit_steps=2, noise=noise, return_samples=True)
+        a = a.cpu()
+        assert a[1].item() == B * (cfg.T - 1) * cfg.S
+        assert abs(a[0].item() / a[1].item() - loss) < 1e-4
+        assert torch.equal(s.cpu(), samples)
+        assert abs(a[3].item() / a[1].item() - acc) < 1e-9
+
+
+PROD = ["genie35m", "genie138m", "genie138m_qknorm_mup"]
+
+
+def _prod_setup(name):
+    z = load_golden(name)
+    kw = golden_cfg(z)
+    cfg = O.OracleConfig(**kw)
+    sd = O.init_state_dict(cfg, seed=int(z["seed"]), readout_gain=1.0, bias_std=0.02)
+    return z, kw, cfg, sd
+
+
+@pytest.mark.parametrize("name", PROD)
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_production_logits_match_reference(name, precision):
+    z, kw, cfg, sd = _prod_setup(name)
+    m = build_b200_model(kw, sd, precision=precision)
+    ids = torch.from_numpy(z["ids"]).long()
+    B = ids.shape[0]
+    logits = m.compute_logits(ids.cuda()).reshape(B, -1, cfg.T, cfg.S)
+    sub = logits[:, :, z["sub_t"].tolist()][:, :, :, z["sub_s"].tolist()].cpu()
+    ref = torch.from_numpy(z["logits_sub"])
+    err = rel_fro(sub, ref)
+    fro = float(torch.linalg.vector_norm(logits.double()))
+    print(f"{name} {precision}: rel(sub) {err:.3e}  fro {fro:.6e} vs ref {float(z['logits_full_fro']):.6e}")
+    assert err < TOL[precision]
+    assert abs(fro - float(z["logits_full_fro"])) / float(z["logits_full_fro"]) < TOL[precision]
+
+
+@pytest.mark.parametrize("name", PROD)
+def test_production_maskgit_argmax_and_tokens(name):
+    z, kw, cfg, sd = _prod_setup(name)
+    ids = torch.from_numpy(z["ids"]).long()
+    B = ids.shape[0]
+    prompt0 = ids.clone()
+    prompt0[:, 8:] = cfg.mask_token_id
+    noise = torch.from_numpy(z["noise"])
+    ref_samples = torch.from_numpy(z["samples"]).long().reshape(B, -1)
+    ref_arg = torch.from_numpy(z["argmax0"]).long()          # [B, NV, S]
+    margin = torch.from_numpy(z["margin0"])                  # [B, NV, S]
+    l0_sub_ref = torch.from_numpy(z["logits0_sub"])          # [B, V, NV, 4]
+    results = {}
+    for precision, kv in [("bf16", False), ("bf16", True), ("fp32", False)]:
+        m = build_b200_model(kw, sd, precision=precision, kv_cache=kv)
+        p = prompt0.clone().cuda()
+        samples, fl = m.maskgit_generate(p, 8, maskgit_steps=2, temperature=0.0, noise=noise)
+        fl = fl.reshape(B, cfg.factored_vocab_size, cfg.num_factored_vocabs, cfg.S).cpu()
+        sub = fl[:, :, :, z["sub_s"].tolist()]
+        max_abs = float((sub - l0_sub_ref).abs().max())
+        arg = fl.argmax(dim=1)
+        solid = margin > 4 * max_abs
+        mism_solid = int(((arg != ref_arg) & solid).sum())
+        mism_all = int((arg != ref_arg).sum())
+        tok_equal = float((samples.reshape(B, -1).cpu() == ref_samples).float().mean())
+        print(f"{name} {precision} kv={kv}: logits0 max|d| {max_abs:.3e}, argmax mismatches {mism_all} "
+              f"(of which margin>4*err: {mism_solid}) / {arg.numel()}, final token agreement {tok_equal:.4f}")
+        assert mism_solid == 0
+        results[(precision, kv)] = (samples.cpu(), fl)
+        if precision == "fp32":
+            assert torch.equal(samples.reshape(B, -1).cpu(), ref_samples)     # bit-exact ids in the exact mode
+            assert torch.equal(p.cpu().reshape(B, -1), torch.from_numpy(z["prompt_after"]).long().reshape(B, -1))
+        else:
+            assert tok_equal > 0.85
+    # the K/V-cached, frame-trimmed path must reproduce the dense path bit for bit
+    assert torch.equal(results[("bf16", False)][0], results[("bf16", True)][0])
+    assert torch.equal(results[("bf16", False)][1], results[("bf16", True)][1])
+
+
+def test_fast_vs_generic_attention_kernels():
+    z, kw, cfg, sd = _prod_setup("genie138m_qknorm_mup")
+    ids = torch.from_numpy(z["ids"]).long().cuda()
+    a = build_b200_model(kw, sd, precision="bf16").compute_logits(ids)
+    b = build_b200_model(kw, sd, precision="bf16", generic_attention=True).compute_logits(ids)
+    err = rel_fro(a, b)
+    print("fast vs generic attention rel", err)
+    assert err < 5e-3
+
+
+def test_reference_attention_cases():
+    """The reference's only test (test_attention.py): heads=4, x=randn(1,16,d), causal, 5 (d, qk_norm) cases."""
+    g = importlib.import_module("1xgpt_b200")
+    for d_model, qk in [(32, False), (64, True), (64, False), (128, True), (128, False)]:
+        z = load_golden(f"attn_d{d_model}_qk{int(qk)}")
+        cfgk = dict(num_layers=1, num_heads=4, d_model=d_model, T=16, S=16, num_factored_vocabs=2, qk_norm=qk,
+                    use_mup=True)
+        m = g.STMaskGIT(g.GenieConfig(**cfgk), precision="fp32")
+        m.init_weights()
+        att = m.decoder.layers[0].temporal_attn
+        att.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")})
+        m = m.to("cuda")
+        m.mark_weights_dirty()
+        x = torch.from_numpy(z["x"]).cuda()
+        y1 = m.decoder.layers[0].temporal_attn(x, causal=True)
+        y2 = m.decoder.layers[0].temporal_attn(x, causal=False)
+        assert torch.allclose(y1.cpu(), torch.from_numpy(z["y_causal"]), atol=2e-6)   # reference: atol 1e-6 on GPU
+        assert torch.allclose(y2.cpu(), torch.from_numpy(z["y_full"]), atol=2e-6)
+
+
+def test_decoder_forward_seam():
+    z = load_golden("tiny_qknorm")
+    kw, sd = golden_cfg(z), golden_sd(z)
+    cfg = O.OracleConfig(**kw)
+    m = build_b200_model(kw, sd, precision="fp32")
+    x = torch.randn(3, cfg.T, cfg.S, cfg.d_model, generator=torch.Generator().manual_seed(5))
+    y = m.decoder(x.cuda())
+    ref = O.decoder_forward(sd, cfg, x)
+    assert rel_fro(y, ref) < 2e-5
+
+
+def test_error_behaviour_matches_reference():
+    z = load_golden("tiny_preln")
+    kw, sd = golden_cfg(z), golden_sd(z)
+    m = build_b200_model(kw, sd, precision="fp32")
+    prompt = torch.from_numpy(z["prompt"]).cuda()
+    with pytest.raises(AssertionError, match="requires out_t > 0"):
+        m.maskgit_generate(prompt.clone(), 0)
+    bad = torch.from_numpy(z["ids"]).cuda()            # frames >= out_t not masked
+    before = bad.clone()
+    with pytest.raises(AssertionError, match="must be masked"):
+        m.maskgit_generate(bad, 2)
+    assert torch.equal(bad, before)                    # untouched on failure
+    with pytest.raises(NotImplementedError, match="unmask_mode"):
+        m.maskgit_generate(prompt.clone(), 2, unmask_mode="bogus")
