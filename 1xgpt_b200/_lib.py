@@ -50,6 +50,8 @@ SIGNATURES = {
     "gn_sample_tokens": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "gn_remask_step": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "gn_cross_entropy": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "gn_profile_begin": (_i, []),
+    "gn_profile_end": (_i, [C.POINTER(C.c_double)]),
     "gn_kernel_launches": (C.c_uint64, []),
     "gn_model_flops_per_clip_forward": (C.c_double, [_vp]),
     "gn_model_flops_executed": (C.c_double, [_vp]),

@@ -2,10 +2,41 @@
 #include "gemm.cuh"
 #include "ptx.cuh"
 #include "tensormap.cuh"
+#include <vector>
 
 namespace gn {
 
 unsigned long long g_launch_count = 0;
+
+namespace {
+struct GemmProfiler {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;   // pairs (start, stop)
+  size_t used = 0;
+  double flops = 0.0;
+} g_prof;
+}  // namespace
+
+int profile_begin() {
+  g_prof.on = true;
+  g_prof.used = 0;
+  g_prof.flops = 0.0;
+  return GN_OK;
+}
+int profile_end(double out[3]) {
+  g_prof.on = false;
+  double ms = 0.0;
+  for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+    GN_CUDA_CHECK(cudaEventSynchronize(g_prof.ev[i + 1]));
+    float t = 0.f;
+    GN_CUDA_CHECK(cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]));
+    ms += t;
+  }
+  out[0] = ms;
+  out[1] = g_prof.flops;
+  out[2] = (double)(g_prof.used / 2);
+  return GN_OK;
+}
 
 // =====================================================================================
 // tcgen05 path
@@ -283,7 +314,21 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
   sms = cached_sms > 0 ? cached_sms : 148;
   const int grid = num_tiles < sms ? num_tiles : sms;
   TcArgs t{a.M, a.N, a.K, a.bias, a.resid, a.ldr, a.round_out_tf32};
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_prof.on) {
+    while (g_prof.ev.size() < g_prof.used + 2) {
+      cudaEvent_t e;
+      GN_CUDA_CHECK(cudaEventCreate(&e));
+      g_prof.ev.push_back(e);
+    }
+    e0 = g_prof.ev[g_prof.used];
+    e1 = g_prof.ev[g_prof.used + 1];
+    g_prof.used += 2;
+    g_prof.flops += 2.0 * a.M * (double)a.N * a.K;
+    GN_CUDA_CHECK(cudaEventRecord(e0, stream));
+  }
   kern<<<grid, GEMM_THREADS, SM::TOTAL, stream>>>(tmA, tmB, tmO, tmO2, t);
+  if (e1) GN_CUDA_CHECK(cudaEventRecord(e1, stream));
   GN_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;
   return GN_OK;

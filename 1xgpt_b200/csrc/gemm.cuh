@@ -39,6 +39,12 @@ struct LinearArgs {
 // Enqueue on `stream`.  Returns GN_OK or a negative code (message via last_error()).
 int linear_forward(const LinearArgs& a, cudaStream_t stream);
 
+// Live per-launch timing of the tcgen05 GEMM kernel (bench.py's roofline leg): while enabled, every tensor-path
+// launch is bracketed by CUDA events on its own stream.  profile_end() synchronises those events and returns
+// {sum of durations [ms], sum of 2*M*N*K, launches} for the launches since profile_begin().
+int profile_begin();
+int profile_end(double out[3]);
+
 // number of kernels launched by linear_forward so far (bench's gpu_launches accounting)
 extern unsigned long long g_launch_count;
 

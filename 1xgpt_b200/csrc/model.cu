@@ -747,6 +747,12 @@ int gn_cross_entropy(const float* logits_rows, const int32_t* targets, int R, in
   return launch_ce(logits_rows, targets, 0, R, R, V, NV, weight, acc, (cudaStream_t)stream);
 }
 
+int gn_profile_begin(void) { return gn::profile_begin(); }
+int gn_profile_end(double* out3) {
+  GN_REQUIRE(out3, "gn_profile_end: null output");
+  return gn::profile_end(out3);
+}
+
 double gn_model_flops_per_clip_forward(gn_model* m) {
   if (!m) return 0.0;
   const gn_config& c = m->cfg;

@@ -128,6 +128,11 @@ int gn_remask_step(int32_t* prompt_frame, int64_t clip_stride, const int32_t* sa
 int gn_cross_entropy(const float* logits_rows, const int32_t* targets, int R, int V, int NV, const uint8_t* weight,
                      double* acc, void* stream);
 
+/* Live timing of the tcgen05 linear-layer kernel (bench.py roofline leg): between begin and end every
+ * tensor-path GEMM launch is bracketed by CUDA events on its stream; out3 = {sum ms, sum 2*M*N*K, launches}. */
+int gn_profile_begin(void);
+int gn_profile_end(double* out3);
+
 /* counters for bench accounting */
 uint64_t gn_kernel_launches(void);              /* kernels launched by this library since load */
 double gn_model_flops_per_clip_forward(gn_model* m); /* dense reference-equivalent FLOPs */

@@ -1,0 +1,97 @@
+"""Host-side mirror of the reference interface: config JSON, state_dict keys, checkpoint I/O, error behaviour.
+No GPU: nothing here launches a kernel."""
+import importlib
+import json
+import os
+
+import pytest
+import torch
+
+from helpers import O, golden_cfg, golden_sd, load_golden
+
+pkg = importlib.import_module("1xgpt_b200")
+REF_35M_JSON = ('{"num_layers": 32, "num_heads": 8, "d_model": 256, "T": 16, "S": 256, "image_vocab_size": 262144, '
+                '"use_mup": false, "num_factored_vocabs": 2, "qkv_bias": false, "proj_bias": true, "attn_drop": 0.0, '
+                '"qk_norm": false, "mlp_ratio": 4.0, "mlp_drop": 0.0, "mlp_bias": true}')
+
+
+def test_reference_config_json_loads_unchanged(tmp_path):
+    p = tmp_path / "magvit_n32_h8_d256.json"
+    p.write_text(REF_35M_JSON)                    # content of genie/configs/magvit_n32_h8_d256.json
+    cfg = pkg.GenieConfig.from_pretrained(str(p))
+    assert (cfg.num_layers, cfg.d_model, cfg.num_heads, cfg.factored_vocab_size) == (32, 256, 8, 512)
+    cfg.save_pretrained(str(tmp_path / "out.json"))
+    again = json.load(open(tmp_path / "out.json"))
+    assert again["factored_vocab_size"] == 512 and again["qk_norm"] is False
+
+
+@pytest.mark.parametrize("name", ["tiny_preln", "tiny_qknorm_mup"])
+def test_state_dict_keys_match_reference(name):
+    z = load_golden(name)
+    kw, sd = golden_cfg(z), golden_sd(z)          # key set produced by the reference's own state_dict()
+    m = pkg.STMaskGIT(pkg.GenieConfig(**kw))
+    assert sorted(m.state_dict().keys()) == sorted(sd.keys())
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    m.load_state_dict(sd, strict=True)
+
+
+def test_checkpoint_roundtrip_hf_layout(tmp_path):
+    z = load_golden("tiny_qknorm")
+    kw, sd = golden_cfg(z), golden_sd(z)
+    m = pkg.STMaskGIT(pkg.GenieConfig(**kw))
+    m.load_state_dict(sd)
+    m.save_pretrained(str(tmp_path))
+    assert sorted(os.listdir(tmp_path)) == ["config.json", "model.safetensors"]
+    m2 = pkg.STMaskGIT.from_pretrained(str(tmp_path), precision="tf32", kv_cache=True)
+    assert m2.precision == "tf32" and m2.kv_cache
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v, sd[k])
+    # HF mixin variant that nests the dataclass under "config"
+    cfgd = json.load(open(tmp_path / "config.json"))
+    json.dump({"config": cfgd}, open(tmp_path / "config.json", "w"))
+    assert pkg.STMaskGIT.from_pretrained(str(tmp_path)).config.d_model == kw["d_model"]
+
+
+def test_no_cpu_fallback_and_argument_errors():
+    z = load_golden("tiny_preln")
+    kw, sd = golden_cfg(z), golden_sd(z)
+    m = pkg.STMaskGIT(pkg.GenieConfig(**kw))
+    m.load_state_dict(sd)
+    ids = torch.from_numpy(z["prompt"])
+    with pytest.raises(pkg.GnError, match="no CPU fallback"):
+        m.compute_logits(ids)
+    with pytest.raises(AssertionError, match="requires out_t > 0"):
+        m.maskgit_generate(ids.clone(), 0)
+    with pytest.raises(NotImplementedError, match="unmask_mode"):
+        m.maskgit_generate(ids.clone(), 2, unmask_mode="nope")
+    with pytest.raises(NotImplementedError, match="temperature"):
+        m.maskgit_generate(ids.clone(), 2, temperature=1.0)
+    with pytest.raises(AssertionError, match="multiple of"):
+        m.generate(ids[:, :2].reshape(2, -1), None, max_new_tokens=7)
+    with pytest.raises(ValueError):
+        pkg.STMaskGIT(pkg.GenieConfig(**kw), precision="fp8")
+    with pytest.raises(RuntimeError, match="parameter container"):
+        pkg.SelfAttention(4, 64)(torch.zeros(1, 4, 64))
+
+
+def test_integer_helpers_match_oracle():
+    ids = torch.randint(0, 262144, (2, 4, 4, 4), generator=torch.Generator().manual_seed(3))
+    assert torch.equal(pkg.factorize_token_ids(ids), O.factorize_token_ids(ids, 2, 512))
+    assert torch.equal(pkg.unfactorize_token_ids(pkg.factorize_token_ids(ids)), ids)
+    assert torch.equal(pkg.factorize_labels(ids), O.factorize_labels(ids, 2, 512))
+    assert pkg.nth_root(262144, 2) == 512
+
+
+def test_generate_writer_reference_format(tmp_path):
+    gen = importlib.import_module("1xgpt_b200.generate")
+    ex = torch.arange(16 * 4 * 4).reshape(16, 4, 4)
+    g = ex + 1000
+    out = gen.write_reference_format(tmp_path, ex, g, 8, {"s": 4, "vocab_size": 262144, "hz": 30, "token_dtype": "uint32"},
+                                     {"maskgit_steps": 2})
+    assert out.shape[0] == 24                                  # 8 prompt + 8 generated + 8 ground truth
+    meta = json.load(open(tmp_path / "metadata.json"))
+    assert meta["num_images"] == 24 and meta["t"] == 16 and meta["h"] == 4 and meta["maskgit_steps"] == 2
+    import numpy as np
+    raw = np.fromfile(tmp_path / "video.bin", dtype=np.uint32).reshape(24, 4, 4)
+    assert (raw[8:16] == g[8:].numpy()).all() and (raw[16:] == ex[8:].numpy()).all()
