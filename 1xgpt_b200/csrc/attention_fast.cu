@@ -113,6 +113,8 @@ spatial_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait();
+  pdl_trigger();
   if (tid == 0) {
     mbar_arrive_expect_tx(&bars[0], (SP_QROWS + S) * ROWB);
     tma_load_2d(sQ, &tmQ, &bars[0], h * HD, q_row0);
@@ -240,9 +242,8 @@ int launch_spatial_t(const AttnArgs& a, int n_frames, int S, cudaStream_t st) {
     set = smem;
   }
   dim3 grid(S / SP_QROWS, a.n_heads, n_frames);
-  kern<<<grid, SP_THREADS, smem, st>>>(tmQ, tmKV, static_cast<bf16*>(a.out), S, d, a.scale * 1.4426950408889634f,
-                                       a.qk_gamma, a.qk_beta);
-  GN_CUDA_CHECK(cudaGetLastError());
+  GN_CUDA_CHECK(launch_kernel(PC_SPATIAL, kern, grid, dim3(SP_THREADS), (size_t)smem, st, tmQ, tmKV, static_cast<bf16*>(a.out), S, d,
+                              a.scale * 1.4426950408889634f, a.qk_gamma, a.qk_beta));
   ++g_launch_count;
   return GN_OK;
 }
@@ -267,34 +268,50 @@ temporal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, bf16*
   uint8_t* sK = sQ + TILEB;
   uint8_t* sV = sK + TILEB;
   const int Tk = t0 + Tq;
+  pdl_wait();
+  pdl_trigger();
   const int64_t fresh0 = ((int64_t)b * Tq) * S + sp;     // fresh row of local frame tl: fresh0 + tl*S
-  const int64_t cache0 = ((int64_t)b * T) * S + sp;      // cache row of frame j: cache0 + j*S
+  const int64_t cache0 = ((int64_t)b * S + sp) * T;      // cache row of frame j: cache0 + j  ([B,S,T,d]: the
+                                                         // frames of one position are contiguous)
 
+  // Phase 1: issue EVERY global load of this warp (q, k, v rows of up to 16 frames) before the first store, so the
+  // whole tile is one round trip to HBM/L2 instead of one per unrolled iteration (the cache update below
+  // aliases kcache/vcache from the compiler's point of view and would otherwise serialise the iterations).
+  constexpr int NIT = 16 * CH / 32;
+  uint4 qv[NIT], kv[NIT], vv[NIT];
 #pragma unroll
-  for (int it = 0; it < 16 * CH / 32; ++it) {
+  for (int it = 0; it < NIT; ++it) {
     const int idx = it * 32 + lane;
     const int r = idx / CH, c = idx % CH;
-    uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q;
-    if (r < Tq) q = *reinterpret_cast<const uint4*>(qkv + (fresh0 + (int64_t)r * S) * 3 * d + h * HD + c * 8);
+    qv[it] = make_uint4(0, 0, 0, 0);
+    kv[it] = qv[it];
+    vv[it] = qv[it];
+    if (r < Tq) qv[it] = __ldg(reinterpret_cast<const uint4*>(qkv + (fresh0 + (int64_t)r * S) * 3 * d + h * HD + c * 8));
     if (r < Tk) {
       if (r < t0) {
-        const int64_t cr = (cache0 + (int64_t)r * S) * d + h * HD + c * 8;
-        k = *reinterpret_cast<const uint4*>(kcache + cr);
-        v = *reinterpret_cast<const uint4*>(vcache + cr);
+        const int64_t cr = (cache0 + r) * d + h * HD + c * 8;
+        kv[it] = *reinterpret_cast<const uint4*>(kcache + cr);
+        vv[it] = *reinterpret_cast<const uint4*>(vcache + cr);
       } else {
         const int64_t fr = (fresh0 + (int64_t)(r - t0) * S) * 3 * d + h * HD + c * 8;
-        k = *reinterpret_cast<const uint4*>(qkv + fr + d);
-        v = *reinterpret_cast<const uint4*>(qkv + fr + 2 * d);
-        if (kcache != nullptr) {
-          const int64_t cr = (cache0 + (int64_t)r * S) * d + h * HD + c * 8;
-          *reinterpret_cast<uint4*>(kcache + cr) = k;
-          *reinterpret_cast<uint4*>(vcache + cr) = v;
-        }
+        kv[it] = __ldg(reinterpret_cast<const uint4*>(qkv + fr + d));
+        vv[it] = __ldg(reinterpret_cast<const uint4*>(qkv + fr + 2 * d));
       }
     }
-    *reinterpret_cast<uint4*>(sQ + swz<HD>(r, c)) = q;
-    *reinterpret_cast<uint4*>(sK + swz<HD>(r, c)) = k;
-    *reinterpret_cast<uint4*>(sV + swz<HD>(r, c)) = v;
+  }
+  // Phase 2: stage in shared memory, append the fresh frames to the K/V cache
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int idx = it * 32 + lane;
+    const int r = idx / CH, c = idx % CH;
+    if (kcache != nullptr && r >= t0 && r < Tk) {
+      const int64_t cr = (cache0 + r) * d + h * HD + c * 8;
+      *reinterpret_cast<uint4*>(kcache + cr) = kv[it];
+      *reinterpret_cast<uint4*>(vcache + cr) = vv[it];
+    }
+    *reinterpret_cast<uint4*>(sQ + swz<HD>(r, c)) = qv[it];
+    *reinterpret_cast<uint4*>(sK + swz<HD>(r, c)) = kv[it];
+    *reinterpret_cast<uint4*>(sV + swz<HD>(r, c)) = vv[it];
   }
   __syncwarp();
   if (gamma != nullptr) {
@@ -394,10 +411,10 @@ int launch_temporal_t(const AttnArgs& a, int B, int S, int T, int t0, int Tq, vo
     GN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     set = smem;
   }
-  kern<<<B * S, a.n_heads * 32, smem, st>>>(static_cast<const bf16*>(a.qkv), static_cast<bf16*>(a.out),
-                                            static_cast<bf16*>(kcache), static_cast<bf16*>(vcache), S, T, t0, Tq, d,
-                                            a.scale * 1.4426950408889634f, a.qk_gamma, a.qk_beta);
-  GN_CUDA_CHECK(cudaGetLastError());
+  GN_CUDA_CHECK(launch_kernel(PC_TEMPORAL, kern, dim3(B * S), dim3(a.n_heads * 32), (size_t)smem, st,
+                              static_cast<const bf16*>(a.qkv), static_cast<bf16*>(a.out), static_cast<bf16*>(kcache),
+                              static_cast<bf16*>(vcache), S, T, t0, Tq, d, a.scale * 1.4426950408889634f, a.qk_gamma,
+                              a.qk_beta));
   ++g_launch_count;
   return GN_OK;
 }

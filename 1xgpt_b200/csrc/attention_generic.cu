@@ -14,7 +14,7 @@ namespace {
 struct GenericMap {
   int inner;                 // seq -> (b = seq / inner, s = seq % inner)
   int64_t q_outer, q_tok;    // fresh row = b*q_outer + s + i*q_tok
-  int64_t c_outer, c_tok;    // cache row = b*c_outer + s + j*c_tok
+  int64_t c_outer, c_inner, c_tok;  // cache row = b*c_outer + s*c_inner + j*c_tok
 };
 
 template <typename T>
@@ -62,7 +62,7 @@ generic_attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, const T
   const int seq = blockIdx.x, h = blockIdx.y;
   const int b = seq / mp.inner, s = seq % mp.inner;
   const int64_t qbase = (int64_t)b * mp.q_outer + s;
-  const int64_t cbase = (int64_t)b * mp.c_outer + s;
+  const int64_t cbase = (int64_t)b * mp.c_outer + (int64_t)s * mp.c_inner;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   for (int j = warp; j < nk; j += 4) {
@@ -167,14 +167,14 @@ int launch_generic_t(const AttnArgs& a, int n_seq, GenericMap mp, int nq, int nk
 }  // namespace
 
 int launch_generic_attention(const AttnArgs& a, int n_seq, int n_tok, int causal, cudaStream_t st) {
-  GenericMap mp{1, n_tok, 1, 0, 0};
+  GenericMap mp{1, n_tok, 1, 0, 0, 0};
   return a.act_bf16 ? launch_generic_t<bf16>(a, n_seq, mp, n_tok, 0, causal, nullptr, nullptr, nullptr, nullptr, st)
                     : launch_generic_t<float>(a, n_seq, mp, n_tok, 0, causal, nullptr, nullptr, nullptr, nullptr, st);
 }
 
 int generic_temporal_attention(const AttnArgs& a, int B, int S, int T, int t0, int Tq, void* kcache, void* vcache,
                                cudaStream_t st) {
-  GenericMap mp{S, (int64_t)Tq * S, S, (int64_t)T * S, S};
+  GenericMap mp{S, (int64_t)Tq * S, S, (int64_t)S * T, T, 1};   // cache layout [B, S, T, d]
   GN_REQUIRE(t0 == 0 || (kcache && vcache), "temporal attention with t0 > 0 needs the K/V caches");
   return a.act_bf16 ? launch_generic_t<bf16>(a, B * S, mp, Tq, t0, 1, kcache, vcache, kcache, vcache, st)
                     : launch_generic_t<float>(a, B * S, mp, Tq, t0, 1, kcache, vcache, kcache, vcache, st);

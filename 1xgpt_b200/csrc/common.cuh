@@ -48,6 +48,40 @@ const char* last_error();
     if (_rc != 0) return _rc;   \
   } while (0)
 
+// Programmatic dependent launch (PDL).  Kernels of the forward chain are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization (when enabled): kernel N+1 may be scheduled and run its
+// prologue (barrier init, TMEM allocation, descriptor prefetch) while kernel N drains; it must not touch global
+// memory before pdl_wait().  pdl_wait() is a no-op for a kernel launched without the attribute.
+extern bool g_use_pdl;
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Live per-launch timing (bench.py): while profiling is on, every launch_kernel() call is bracketed by CUDA
+// events on its stream and accounted to a category.
+enum ProfCat : int { PC_GEMM_STORE = 0, PC_GEMM_GELU, PC_GEMM_RESID, PC_PREP, PC_SPATIAL, PC_TEMPORAL, PC_OTHER, PC_COUNT };
+void prof_before(int cat, cudaStream_t st);
+void prof_after(cudaStream_t st);
+extern bool g_prof_on;
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(int cat, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+  if (g_prof_on) prof_before(cat, st);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  if (g_prof_on) prof_after(st);
+  return e;
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -87,5 +121,72 @@ __device__ __forceinline__ float tf32_rn(float x) {
 
 // exact-erf GELU (nn.GELU() default, st_transformer.py:17)
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+
+// GELU for bf16 outputs: erfc(|x|/sqrt2) = 2^q(|x|) with a degree-5 polynomial q (no constant term), fitted on
+// [0, 6] (weighted minimax, scripts in DESIGN.md); max |gelu_fast - gelu_erf| = 5.4e-7, relative error <= 4e-4
+// wherever |gelu| > 1e-3 (and ~1e-6 for x > 0): two orders below the bf16 rounding of the stored value.
+// 1 MUFU (ex2) + 9 FP32 ops instead of erff's ~40.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fminf(fabsf(x), 6.0f);
+  float q = fmaf(-4.88107450e-04f, z, 7.19873621e-03f);
+  q = fmaf(q, z, -5.21466308e-02f);
+  q = fmaf(q, z, -4.59595885e-01f);
+  q = fmaf(q, z, -1.15100052e+00f);
+  q *= z;
+  float e;                             // erfc(|x|/sqrt2) in (0, 1]; q in [-31, 0]: no denormal handling needed
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
+  const float h = 0.5f * x;
+  const float ah = fabsf(h);
+  return h + fmaf(-ah, e, ah);         // 0.5x + 0.5|x| (1 - erfc)
+}
+
+
+// ---- packed fp32x2 arithmetic (sm_100: one FFMA2 does two FMAs; the scalar 3-register FFMA issues at half rate)
+__device__ __forceinline__ uint64_t pack_f2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// gelu_fast on two values at once (same polynomial), fma-pipe work done with packed instructions
+__device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
+  const float z0 = fminf(fabsf(x0), 6.0f), z1 = fminf(fabsf(x1), 6.0f);
+  const uint64_t z = pack_f2(z0, z1);
+  uint64_t q = fma2(pack_f2(-4.88107450e-04f, -4.88107450e-04f), z, pack_f2(7.19873621e-03f, 7.19873621e-03f));
+  q = fma2(q, z, pack_f2(-5.21466308e-02f, -5.21466308e-02f));
+  q = fma2(q, z, pack_f2(-4.59595885e-01f, -4.59595885e-01f));
+  q = fma2(q, z, pack_f2(-1.15100052e+00f, -1.15100052e+00f));
+  q = mul2(q, z);
+  float q0, q1, e0, e1;
+  unpack_f2(q, q0, q1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q1));
+  const uint64_t x = pack_f2(x0, x1);
+  const uint64_t h = mul2(x, pack_f2(0.5f, 0.5f));
+  float h0, h1;
+  unpack_f2(h, h0, h1);
+  const uint64_t ah = pack_f2(fabsf(h0), fabsf(h1));
+  const uint64_t t = fma2(pack_f2(e0, e1), pack_f2(-1.0f, -1.0f), pack_f2(1.0f, 1.0f));   // 1 - erfc
+  unpack_f2(fma2(ah, t, h), x0, x1);
+}
 
 }  // namespace gn

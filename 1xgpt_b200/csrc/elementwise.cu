@@ -69,6 +69,8 @@ __global__ void __launch_bounds__(256)
 prep_kernel(const float* __restrict__ x, OutT* __restrict__ out, const float* __restrict__ gamma,
             const float* __restrict__ beta, int n_rows, int d, float eps, float scale, int S, int Tact, int tsel,
             int round_tf32) {
+  pdl_wait();
+  pdl_trigger();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n_rows) return;
   const int lane = threadIdx.x & 31;
@@ -134,13 +136,13 @@ static int launch_prep_t(const float* x, OutT* out, const float* gamma, const fl
   const int grid = ceil_div(n_rows, wpb);
   const int nvec = d / 4;
   if (nvec <= 32 * 2)
-    prep_kernel<OutT, 2><<<grid, wpb * 32, 0, st>>>(x, out, gamma, beta, n_rows, d, 1e-5f, scale, S, Tact, tsel, round_tf32);
+    GN_CUDA_CHECK(launch_kernel(PC_PREP, prep_kernel<OutT, 2>, dim3(grid), dim3(wpb * 32), 0, st, x, out, gamma, beta, n_rows, d, 1e-5f, scale, S, Tact, tsel, round_tf32));
   else if (nvec <= 32 * 4)
-    prep_kernel<OutT, 4><<<grid, wpb * 32, 0, st>>>(x, out, gamma, beta, n_rows, d, 1e-5f, scale, S, Tact, tsel, round_tf32);
+    GN_CUDA_CHECK(launch_kernel(PC_PREP, prep_kernel<OutT, 4>, dim3(grid), dim3(wpb * 32), 0, st, x, out, gamma, beta, n_rows, d, 1e-5f, scale, S, Tact, tsel, round_tf32));
   else if (nvec <= 32 * 8)
-    prep_kernel<OutT, 8><<<grid, wpb * 32, 0, st>>>(x, out, gamma, beta, n_rows, d, 1e-5f, scale, S, Tact, tsel, round_tf32);
+    GN_CUDA_CHECK(launch_kernel(PC_PREP, prep_kernel<OutT, 8>, dim3(grid), dim3(wpb * 32), 0, st, x, out, gamma, beta, n_rows, d, 1e-5f, scale, S, Tact, tsel, round_tf32));
   else if (nvec <= 32 * 16)
-    prep_kernel<OutT, 16><<<grid, wpb * 32, 0, st>>>(x, out, gamma, beta, n_rows, d, 1e-5f, scale, S, Tact, tsel, round_tf32);
+    GN_CUDA_CHECK(launch_kernel(PC_PREP, prep_kernel<OutT, 16>, dim3(grid), dim3(wpb * 32), 0, st, x, out, gamma, beta, n_rows, d, 1e-5f, scale, S, Tact, tsel, round_tf32));
   else {
     set_error("prep: d_model %d > 2048 not supported", d);
     return GN_ERR_UNSUPPORTED;

@@ -8,35 +8,7 @@ namespace gn {
 
 unsigned long long g_launch_count = 0;
 
-namespace {
-struct GemmProfiler {
-  bool on = false;
-  std::vector<cudaEvent_t> ev;   // pairs (start, stop)
-  size_t used = 0;
-  double flops = 0.0;
-} g_prof;
-}  // namespace
-
-int profile_begin() {
-  g_prof.on = true;
-  g_prof.used = 0;
-  g_prof.flops = 0.0;
-  return GN_OK;
-}
-int profile_end(double out[3]) {
-  g_prof.on = false;
-  double ms = 0.0;
-  for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
-    GN_CUDA_CHECK(cudaEventSynchronize(g_prof.ev[i + 1]));
-    float t = 0.f;
-    GN_CUDA_CHECK(cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]));
-    ms += t;
-  }
-  out[0] = ms;
-  out[1] = g_prof.flops;
-  out[2] = (double)(g_prof.used / 2);
-  return GN_OK;
-}
+double g_gemm_flops_issued = 0.0;
 
 // =====================================================================================
 // tcgen05 path
@@ -52,18 +24,23 @@ constexpr int NUM_EPI_WARPS = 4;
 constexpr int GEMM_THREADS = 32 * (2 + NUM_EPI_WARPS);
 constexpr int SMEM_LIMIT = 232448;           // 227 KB opt-in dynamic shared memory per CTA
 
-template <int BLOCK_N, typename OutT, bool DUAL>
+constexpr int RES_BUFS = 4;      // residual epilogue: in-place staging buffers per warp
+constexpr int RES_PREFETCH = 2;  // residual chunks requested ahead of use
+
+template <int BLOCK_N, int EPI, typename OutT, bool DUAL>
 struct GemmSmem {
+  static constexpr int OUT_BUFS = EPI == EPI_RESID ? RES_BUFS : 2;
   static constexpr int B_TILE_BYTES = BLOCK_N * TILE_K_BYTES;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int OUT_STAGE_BYTES = 32 * EPI_COLS * (int)sizeof(OutT);          // per warp per buffer
   static constexpr int OUT2_STAGE_BYTES = DUAL ? 32 * EPI_COLS * 2 : 0;
-  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * 2 * (OUT_STAGE_BYTES + OUT2_STAGE_BYTES);
+  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * (OUT_BUFS * OUT_STAGE_BYTES + 2 * OUT2_STAGE_BYTES);
+  static constexpr int BIAS_BYTES = NUM_EPI_WARPS * BLOCK_N * 4;   // per-warp copy of the tile's bias slice
   static constexpr int BAR_BYTES = 1024;
   static constexpr int ALIGN_SLACK = 1024;
-  static constexpr int RAW_STAGES = (SMEM_LIMIT - STAGING_BYTES - BAR_BYTES - ALIGN_SLACK) / STAGE_BYTES;
+  static constexpr int RAW_STAGES = (SMEM_LIMIT - STAGING_BYTES - BIAS_BYTES - BAR_BYTES - ALIGN_SLACK) / STAGE_BYTES;
   static constexpr int STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + ALIGN_SLACK;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + BIAS_BYTES + BAR_BYTES + ALIGN_SLACK;
   static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
@@ -107,8 +84,8 @@ template <typename InT, int BLOCK_N, int EPI, typename OutT, bool DUAL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
-                    const TcArgs args) {
-  using SM = GemmSmem<BLOCK_N, OutT, DUAL>;
+                    const __grid_constant__ CUtensorMap tmRes, const TcArgs args) {
+  using SM = GemmSmem<BLOCK_N, EPI, OutT, DUAL>;
   constexpr int STAGES = SM::STAGES;
   constexpr int BLOCK_K = TILE_K_BYTES / (int)sizeof(InT);     // 64 (bf16) or 32 (tf32)
   constexpr int TMEM_COLS = NUM_ACC_STAGES * BLOCK_N;          // 128 / 256 / 512
@@ -120,12 +97,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem_a = smem;                                            // STAGES x 16 KB
   uint8_t* smem_b = smem + STAGES * A_TILE_BYTES;                    // STAGES x BLOCK_N*128
   uint8_t* staging = smem + STAGES * SM::STAGE_BYTES;                // epilogue staging
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + SM::STAGING_BYTES);
+  float* bias_smem = reinterpret_cast<float*>(staging + SM::STAGING_BYTES);   // [NUM_EPI_WARPS][BLOCK_N]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + SM::STAGING_BYTES + SM::BIAS_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* acc_full = bars + 2 * STAGES;
   uint64_t* acc_empty = acc_full + NUM_ACC_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NUM_ACC_STAGES);
+  uint64_t* res_bar = acc_empty + NUM_ACC_STAGES;                    // [NUM_EPI_WARPS][RES_BUFS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + NUM_EPI_WARPS * RES_BUFS);
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -140,6 +119,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
     if (DUAL) tma_prefetch_desc(&tmOut2);
+    if (EPI == EPI_RESID) tma_prefetch_desc(&tmRes);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -148,6 +128,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], NUM_EPI_WARPS);
     }
+    for (int s = 0; s < NUM_EPI_WARPS * RES_BUFS; ++s) mbar_init(&res_bar[s], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -155,6 +136,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched only below
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -203,71 +186,158 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------------------------------------------ epilogue warps
     const uint32_t q = warp & 3;                   // TMEM lane quarter this warp may access
     const uint32_t ew = warp - 2;                  // staging slot
-    uint8_t* st0 = staging + ew * 2 * SM::OUT_STAGE_BYTES;
-    uint8_t* st1 = staging + NUM_EPI_WARPS * 2 * SM::OUT_STAGE_BYTES + ew * 2 * SM::OUT2_STAGE_BYTES;
-    uint32_t as = 0, aphase = 0, buf = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
-      const int row0 = m_blk * BLOCK_M + q * 32;
-      const int row = row0 + lane;
-      mbar_wait(&acc_full[as], aphase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / EPI_COLS; ++c) {
-        const int col0 = n_blk * BLOCK_N + c * EPI_COLS;
-        uint32_t r[EPI_COLS];
-        tmem_ld_32x32b_x32(tmem_base + ((q * 32u) << 16) + as * BLOCK_N + c * EPI_COLS, r);
-        tmem_ld_wait();
-        if (c == BLOCK_N / EPI_COLS - 1) {
-          // accumulator stage fully read into registers: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[as]);
+    constexpr int CH = BLOCK_N / EPI_COLS;
+    uint8_t* st0 = staging + ew * SM::OUT_BUFS * SM::OUT_STAGE_BYTES;
+    uint8_t* st1 = staging + NUM_EPI_WARPS * SM::OUT_BUFS * SM::OUT_STAGE_BYTES + ew * 2 * SM::OUT2_STAGE_BYTES;
+    uint32_t as = 0, aphase = 0;
+    float* sbias = bias_smem + ew * BLOCK_N;
+    const bool has_bias = args.bias != nullptr;
+    // stage this tile's bias slice in shared memory (per warp) BEFORE waiting for the accumulator, so the
+    // global-load latency hides behind the MMA of the tile
+    auto stage_bias = [&](int n_blk) {
+      if (has_bias) {
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < BLOCK_N / 32; ++i) sbias[i * 32 + lane] = __ldg(args.bias + n_blk * BLOCK_N + i * 32 + lane);
+        __syncwarp();
+      }
+    };
+    auto add_bias = [&](float (&v)[EPI_COLS], int c) {
+      if (has_bias) {
+        const float4* bp = reinterpret_cast<const float4*>(sbias + c * EPI_COLS);
+#pragma unroll
+        for (int j = 0; j < EPI_COLS / 4; ++j) {
+          const float4 b = bp[j];
+          v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
         }
-        float v[EPI_COLS];
+      }
+    };
+    if constexpr (EPI == EPI_RESID) {
+      // Residual epilogue.  The fp32 residual chunk (32 rows x 32 cols of this warp) is TMA-loaded into a
+      // swizzled staging buffer RES_PREFETCH chunks ahead, updated IN PLACE with acc + bias, and TMA-stored
+      // from the same buffer: every global access of the epilogue is a coalesced bulk copy.
+      uint64_t* rbar = res_bar + ew * RES_BUFS;
+      const int my_tiles = (int)blockIdx.x < num_tiles ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+      const int total_chunks = my_tiles * CH;
+      auto issue_residual = [&](int g) {           // lane 0 only
+        const int t = blockIdx.x + (g / CH) * gridDim.x;
+        const int mb = t / num_n, nb = t % num_n;
+        const int b = g % RES_BUFS;
+        mbar_arrive_expect_tx(&rbar[b], SM::OUT_STAGE_BYTES);
+        tma_load_2d(st0 + b * SM::OUT_STAGE_BYTES, &tmRes, &rbar[b], nb * BLOCK_N + (g % CH) * EPI_COLS,
+                    mb * BLOCK_M + q * 32);
+      };
+      if (lane == 0) {
+        for (int g0 = 0; g0 < RES_PREFETCH && g0 < total_chunks; ++g0) issue_residual(g0);
+      }
+      int g = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        const int row0 = m_blk * BLOCK_M + q * 32;
+        stage_bias(n_blk);
+        mbar_wait(&acc_full[as], aphase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < CH; ++c, ++g) {
+          const int col0 = n_blk * BLOCK_N + c * EPI_COLS;
+          if (lane == 0) {
+            // buffer (g + PREFETCH) % BUFS was last stored from RES_BUFS - RES_PREFETCH chunks ago
+            tma_store_wait_read<RES_BUFS - RES_PREFETCH - 1>();
+            if (g + RES_PREFETCH < total_chunks) issue_residual(g + RES_PREFETCH);
+          }
+          uint32_t r[EPI_COLS];
+          tmem_ld_32x32b_x32(tmem_base + ((q * 32u) << 16) + as * BLOCK_N + c * EPI_COLS, r);
+          tmem_ld_wait();
+          if (c == CH - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+          }
+          float v[EPI_COLS];
 #pragma unroll
-        for (int j = 0; j < EPI_COLS; ++j) v[j] = __uint_as_float(r[j]);
-        if (args.bias != nullptr) {
-          const float4* bp = reinterpret_cast<const float4*>(args.bias + col0);
+          for (int j = 0; j < EPI_COLS; ++j) v[j] = __uint_as_float(r[j]);
+          add_bias(v, c);
+          const int b = g % RES_BUFS;
+          mbar_wait(&rbar[b], (g / RES_BUFS) & 1);
+          __syncwarp();                             // lane 0's wait_read above precedes every lane's staging writes
+          uint8_t* rowp = st0 + b * SM::OUT_STAGE_BYTES + lane * 128;
 #pragma unroll
-          for (int j = 0; j < EPI_COLS / 4; ++j) {
-            const float4 b = __ldg(bp + j);
-            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          for (int j = 0; j < 8; ++j) {
+            float4* p = reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4));
+            const float4 x4 = *p;
+            v[4 * j] += x4.x; v[4 * j + 1] += x4.y; v[4 * j + 2] += x4.z; v[4 * j + 3] += x4.w;
+            *p = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (DUAL) stage_row_chunk<bf16>(st1 + (g & 1) * SM::OUT2_STAGE_BYTES, lane, v);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmOut, st0 + b * SM::OUT_STAGE_BYTES, col0, row0);
+            if (DUAL) tma_store_2d(&tmOut2, st1 + (g & 1) * SM::OUT2_STAGE_BYTES, col0, row0);
+            tma_store_commit();
           }
         }
-        if (EPI == EPI_GELU) {
+        if (++as == NUM_ACC_STAGES) { as = 0; aphase ^= 1; }
+      }
+    } else {
+      uint32_t buf = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        const int row0 = m_blk * BLOCK_M + q * 32;
+        stage_bias(n_blk);
+        mbar_wait(&acc_full[as], aphase);
+        tc_fence_after();
+        const uint32_t acc_addr = tmem_base + ((q * 32u) << 16) + as * BLOCK_N;
+        uint32_t rr[2][EPI_COLS];
+        tmem_ld_32x32b_x32(acc_addr, rr[0]);
+        // one chunk: wait for its TMEM load, start the next chunk's load (overlaps the math), bias / activation,
+        // swizzled staging, TMA store
+        auto do_chunk = [&](uint32_t (&r)[EPI_COLS], uint32_t (&rnext)[EPI_COLS], int c) {
+          const int col0 = n_blk * BLOCK_N + c * EPI_COLS;
+          tmem_ld_wait();
+          if (c + 1 < CH) tmem_ld_32x32b_x32(acc_addr + (c + 1) * EPI_COLS, rnext);
+          if (c == CH - 1) {
+            // accumulator stage fully read into registers: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+          }
+          float v[EPI_COLS];
 #pragma unroll
-          for (int j = 0; j < EPI_COLS; ++j) v[j] = gelu_erf(v[j]);
-        }
-        if (sizeof(OutT) == 4 && EPI != EPI_RESID && args.round_tf32) {
+          for (int j = 0; j < EPI_COLS; ++j) v[j] = __uint_as_float(r[j]);
+          add_bias(v, c);
+          if (EPI == EPI_GELU) {
+            if (sizeof(OutT) == 2) {
 #pragma unroll
-          for (int j = 0; j < EPI_COLS; ++j) v[j] = tf32_rn(v[j]);
-        }
-        if (EPI == EPI_RESID) {
-          if (row < args.M) {
-            const float4* rp = reinterpret_cast<const float4*>(args.resid + (int64_t)row * args.ldr + col0);
+              for (int j = 0; j < EPI_COLS; j += 2) gelu_fast2(v[j], v[j + 1]);
+            } else {
 #pragma unroll
-            for (int j = 0; j < EPI_COLS / 4; ++j) {
-              const float4 b = rp[j];
-              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+              for (int j = 0; j < EPI_COLS; ++j) v[j] = gelu_erf(v[j]);
             }
           }
+          if (sizeof(OutT) == 4 && args.round_tf32) {
+#pragma unroll
+            for (int j = 0; j < EPI_COLS; ++j) v[j] = tf32_rn(v[j]);
+          }
+          // staging buffer `buf` was last used two steps ago: allow at most one newer bulk group in flight
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          stage_row_chunk<OutT>(st0 + buf * SM::OUT_STAGE_BYTES, lane, v);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmOut, st0 + buf * SM::OUT_STAGE_BYTES, col0, row0);
+            tma_store_commit();
+          }
+          buf ^= 1;
+        };
+#pragma unroll 1
+        for (int c2 = 0; c2 < CH; c2 += 2) {
+          do_chunk(rr[0], rr[1], c2);
+          do_chunk(rr[1], rr[0], c2 + 1);
         }
-        // staging buffer `buf` was last used two steps ago: allow at most one newer bulk group in flight
-        if (lane == 0) tma_store_wait_read<1>();
-        __syncwarp();
-        stage_row_chunk<OutT>(st0 + buf * SM::OUT_STAGE_BYTES, lane, v);
-        if (DUAL) stage_row_chunk<bf16>(st1 + buf * SM::OUT2_STAGE_BYTES, lane, v);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&tmOut, st0 + buf * SM::OUT_STAGE_BYTES, col0, row0);
-          if (DUAL) tma_store_2d(&tmOut2, st1 + buf * SM::OUT2_STAGE_BYTES, col0, row0);
-          tma_store_commit();
-        }
-        buf ^= 1;
+        if (++as == NUM_ACC_STAGES) { as = 0; aphase ^= 1; }
       }
-      if (++as == NUM_ACC_STAGES) { as = 0; aphase ^= 1; }
     }
     if (lane == 0) tma_store_wait_all<0>();
   }
@@ -282,12 +352,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 template <typename InT, int BLOCK_N, int EPI, typename OutT, bool DUAL>
 int launch_tc(const LinearArgs& a, cudaStream_t stream) {
-  using SM = GemmSmem<BLOCK_N, OutT, DUAL>;
+  using SM = GemmSmem<BLOCK_N, EPI, OutT, DUAL>;
   constexpr int BLOCK_K = TILE_K_BYTES / (int)sizeof(InT);
   const CUtensorMapDataType in_dt = sizeof(InT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   const CUtensorMapDataType out_dt =
       sizeof(OutT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  CUtensorMap tmA, tmB, tmO, tmO2;
+  CUtensorMap tmA, tmB, tmO, tmO2, tmR;
   GN_PROPAGATE(make_tensor_map_2d(&tmA, a.A, in_dt, sizeof(InT), a.K, a.M, a.lda, BLOCK_K, BLOCK_M,
                                   CU_TENSOR_MAP_SWIZZLE_128B));
   GN_PROPAGATE(make_tensor_map_2d(&tmB, a.W, in_dt, sizeof(InT), a.K, a.N, a.ldw, BLOCK_K, BLOCK_N,
@@ -299,6 +369,12 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
                                     32, CU_TENSOR_MAP_SWIZZLE_64B));
   } else {
     tmO2 = tmO;
+  }
+  if (EPI == EPI_RESID) {
+    GN_PROPAGATE(make_tensor_map_2d(&tmR, a.resid, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.N, a.M, a.ldr, EPI_COLS, 32,
+                                    CU_TENSOR_MAP_SWIZZLE_128B));
+  } else {
+    tmR = tmO;
   }
   auto kern = gemm_tcgen05_kernel<InT, BLOCK_N, EPI, OutT, DUAL>;
   static bool attr_set = false;
@@ -314,22 +390,9 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
   sms = cached_sms > 0 ? cached_sms : 148;
   const int grid = num_tiles < sms ? num_tiles : sms;
   TcArgs t{a.M, a.N, a.K, a.bias, a.resid, a.ldr, a.round_out_tf32};
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (g_prof.on) {
-    while (g_prof.ev.size() < g_prof.used + 2) {
-      cudaEvent_t e;
-      GN_CUDA_CHECK(cudaEventCreate(&e));
-      g_prof.ev.push_back(e);
-    }
-    e0 = g_prof.ev[g_prof.used];
-    e1 = g_prof.ev[g_prof.used + 1];
-    g_prof.used += 2;
-    g_prof.flops += 2.0 * a.M * (double)a.N * a.K;
-    GN_CUDA_CHECK(cudaEventRecord(e0, stream));
-  }
-  kern<<<grid, GEMM_THREADS, SM::TOTAL, stream>>>(tmA, tmB, tmO, tmO2, t);
-  if (e1) GN_CUDA_CHECK(cudaEventRecord(e1, stream));
-  GN_CUDA_CHECK(cudaGetLastError());
+  g_gemm_flops_issued += 2.0 * a.M * (double)a.N * a.K;
+  const int cat = EPI == EPI_RESID ? PC_GEMM_RESID : (EPI == EPI_GELU ? PC_GEMM_GELU : PC_GEMM_STORE);
+  GN_CUDA_CHECK(launch_kernel(cat, kern, dim3(grid), dim3(GEMM_THREADS), SM::TOTAL, stream, tmA, tmB, tmO, tmO2, tmR, t));
   ++g_launch_count;
   return GN_OK;
 }
@@ -346,8 +409,13 @@ int dispatch_epi(const LinearArgs& a, cudaStream_t s) {
   }
   if (a.epi == EPI_RESID) {
     if (a.out_bf16) { set_error("EPI_RESID writes the fp32 residual stream"); return GN_ERR_INVALID; }
-    return a.out2 ? launch_tc<InT, BLOCK_N, EPI_RESID, float, true>(a, s)
-                  : launch_tc<InT, BLOCK_N, EPI_RESID, float, false>(a, s);
+    if constexpr (BLOCK_N <= 128) {
+      return a.out2 ? launch_tc<InT, BLOCK_N, EPI_RESID, float, true>(a, s)
+                    : launch_tc<InT, BLOCK_N, EPI_RESID, float, false>(a, s);
+    } else {
+      set_error("EPI_RESID is tiled with BLOCK_N <= 128");
+      return GN_ERR_INVALID;
+    }
   }
   set_error("unknown epilogue %d", a.epi);
   return GN_ERR_INVALID;
@@ -435,7 +503,7 @@ int linear_forward(const LinearArgs& a, cudaStream_t stream) {
   const int esz = a.in_bf16 ? 2 : 4;
   const bool tc_ok = !a.force_simt && (a.N % 64 == 0) && (a.K * esz % 16 == 0) && (a.lda * esz % 16 == 0) &&
                      (a.ldw * esz % 16 == 0) && (a.ldo * (a.out_bf16 ? 2 : 4) % 16 == 0) &&
-                     (!a.out2 || a.ldo2 * 2 % 16 == 0) && (!a.resid || a.ldr % 4 == 0) &&
+                     (!a.out2 || a.ldo2 * 2 % 16 == 0) && (!a.resid || a.ldr * 4 % 16 == 0) &&
                      (reinterpret_cast<uintptr_t>(a.A) % 16 == 0) && (reinterpret_cast<uintptr_t>(a.W) % 16 == 0) &&
                      (reinterpret_cast<uintptr_t>(a.out) % 16 == 0) &&
                      (!a.out2 || reinterpret_cast<uintptr_t>(a.out2) % 16 == 0) &&

@@ -43,7 +43,8 @@ int linear_forward(const LinearArgs& a, cudaStream_t stream);
 // launch is bracketed by CUDA events on its own stream.  profile_end() synchronises those events and returns
 // {sum of durations [ms], sum of 2*M*N*K, launches} for the launches since profile_begin().
 int profile_begin();
-int profile_end(double out[3]);
+int profile_end(double* out);   // see runtime.cu: per-category {ms, launches}
+extern double g_gemm_flops_issued;   // 2*M*N*K summed over tensor-path launches (reset by the caller)
 
 // number of kernels launched by linear_forward so far (bench's gpu_launches accounting)
 extern unsigned long long g_launch_count;

@@ -31,7 +31,7 @@ struct AttnArgs {
 // spatial: sequences = frames; tokens of a sequence are S consecutive rows.  non-causal.
 int launch_spatial_attention(const AttnArgs& a, int n_frames, int S, int force_generic, cudaStream_t st);
 // temporal: sequences = (clip, spatial position); token (b, tl, s) is row (b*Tq + tl)*S + s of qkv (fresh
-// frames t0..t0+Tq-1).  Keys/values of frames < t0 come from kcache/vcache [B, T, S, d] (nullptr when t0 == 0);
+// frames t0..t0+Tq-1).  Keys/values of frames < t0 come from kcache/vcache [B, S, T, d] (nullptr when t0 == 0);
 // fresh k/v are written back to the caches when they are non-null.  causal.
 int launch_temporal_attention(const AttnArgs& a, int B, int S, int T, int t0, int Tq, void* kcache, void* vcache,
                               int force_generic, cudaStream_t st);

@@ -68,7 +68,7 @@ struct gn_model {
   int64_t rows_cap = 0;
   float* rows = nullptr;  // [rows_cap, C] fp32 logits rows
 
-  // temporal K/V cache [L][cache_B][T][S][d] act
+  // temporal K/V cache [L][cache_B][S][T][d] act (all frames of one spatial position contiguous)
   int cache_B = 0;
   void* kcache = nullptr;
   void* vcache = nullptr;
@@ -747,10 +747,15 @@ int gn_cross_entropy(const float* logits_rows, const int32_t* targets, int R, in
   return launch_ce(logits_rows, targets, 0, R, R, V, NV, weight, acc, (cudaStream_t)stream);
 }
 
-int gn_profile_begin(void) { return gn::profile_begin(); }
-int gn_profile_end(double* out3) {
-  GN_REQUIRE(out3, "gn_profile_end: null output");
-  return gn::profile_end(out3);
+int gn_profile_begin(void) {
+  gn::g_gemm_flops_issued = 0.0;
+  return gn::profile_begin();
+}
+int gn_profile_end(double* out) {
+  GN_REQUIRE(out, "gn_profile_end: null output");
+  GN_PROPAGATE(gn::profile_end(out));
+  out[2 * gn::PC_COUNT] = gn::g_gemm_flops_issued;
+  return GN_OK;
 }
 
 double gn_model_flops_per_clip_forward(gn_model* m) {

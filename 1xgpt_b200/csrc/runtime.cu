@@ -3,10 +3,62 @@
 #include "tensormap.cuh"
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <cstdlib>
+#include <vector>
 
 namespace gn {
 
 static thread_local char g_err[1024] = "";
+
+static bool env_flag(const char* name, bool dflt) {
+  const char* v = getenv(name);
+  if (!v || !*v) return dflt;
+  return !(v[0] == '0' || v[0] == 'n' || v[0] == 'N' || v[0] == 'f' || v[0] == 'F');
+}
+bool g_use_pdl = env_flag("GENIE_B200_PDL", true);
+
+// ---- live launch profiler
+bool g_prof_on = false;
+namespace {
+struct Prof {
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> cat;
+  size_t used = 0;
+} g_prof;
+}  // namespace
+void prof_before(int cat, cudaStream_t st) {
+  while (g_prof.ev.size() < g_prof.used + 2) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    g_prof.ev.push_back(e);
+  }
+  if (g_prof.cat.size() < g_prof.used / 2 + 1) g_prof.cat.resize(g_prof.used / 2 + 1);
+  g_prof.cat[g_prof.used / 2] = cat;
+  cudaEventRecord(g_prof.ev[g_prof.used], st);
+}
+void prof_after(cudaStream_t st) {
+  cudaEventRecord(g_prof.ev[g_prof.used + 1], st);
+  g_prof.used += 2;
+}
+int profile_begin() {
+  g_prof.used = 0;
+  g_prof_on = true;
+  return GN_OK;
+}
+// out[2*c] = total ms of category c, out[2*c+1] = launches of category c   (c < PC_COUNT)
+int profile_end(double* out) {
+  g_prof_on = false;
+  for (int c = 0; c < 2 * PC_COUNT; ++c) out[c] = 0.0;
+  for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+    GN_CUDA_CHECK(cudaEventSynchronize(g_prof.ev[i + 1]));
+    float t = 0.f;
+    GN_CUDA_CHECK(cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]));
+    const int c = g_prof.cat[i / 2];
+    out[2 * c] += t;
+    out[2 * c + 1] += 1.0;
+  }
+  return GN_OK;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;

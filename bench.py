@@ -198,7 +198,7 @@ def main():
                     help="cached: temporal K/V cache + causal frame trimming (identical tokens); dense: recompute the "
                          "full 16-frame window every MaskGIT step like the reference")
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
-    ap.add_argument("--chunk-tokens", type=int, default=0)
+    ap.add_argument("--chunk-tokens", type=int, default=32768)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary (other mode) measurement")
     args = ap.parse_args()
@@ -269,13 +269,15 @@ def main():
         if profile:
             lib.gn_profile_begin()
         e0.record(stream)
+        t_host = time.perf_counter()
         for _ in range(steps):
             fn(mh)
+        timed.host_enqueue_ms = 1e3 * (time.perf_counter() - t_host) / steps   # CPU time to enqueue one step
         e1.record(stream)
         barrier()
         prof = None
         if profile:
-            out = (C.c_double * 3)()
+            out = (C.c_double * 15)()
             pkg._lib.check(lib.gn_profile_end(out))
             prof = list(out)
         ms = e0.elapsed_time(e1)
@@ -290,6 +292,7 @@ def main():
     with ClockSampler(local) as cs:
         ms, launches, _ = timed(step_device, h, args.steps, args.warmup)
     clocks = cs.summary()
+    host_enqueue_ms = timed.host_enqueue_ms
     flops_exec = model.flops_executed()
     value = frames_per_step * args.steps / (ms / 1e3)
     # ---- the same K steps again with every tcgen05 GEMM launch bracketed by CUDA events on its stream (the event
@@ -301,7 +304,12 @@ def main():
 
     peaks, peak_src = load_peaks()
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-    gemm_ms, gemm_flops, gemm_launches = prof
+    cats = ["gemm_store", "gemm_gelu", "gemm_resid", "prep_ln", "spatial_attn", "temporal_attn", "other"]
+    by_cat = {c: {"ms_per_step": prof[2 * i] / args.steps, "launches_per_step": prof[2 * i + 1] / args.steps}
+              for i, c in enumerate(cats)}
+    gemm_ms = prof[0] + prof[2] + prof[4]
+    gemm_launches = prof[1] + prof[3] + prof[5]
+    gemm_flops = prof[14]
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     dense_flops_step = model.flops_per_clip_forward() * B * n_new * MASKGIT_STEPS  # reference-equivalent FLOPs / step / GPU
 
@@ -344,13 +352,13 @@ def main():
                          "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
                          "kernel": "gemm_tcgen05_kernel (all linear layers)", "launches_timed": int(gemm_launches),
                          "kernel_ms_per_step": gemm_ms / args.steps, "kernel_share_of_step": gemm_ms / ms_prof,
-                         "profiled_ms_per_step": ms_prof / args.steps,
+                         "profiled_ms_per_step": ms_prof / args.steps, "kernel_ms_by_category": by_cat,
                          "peak_source": f"{peak_src} bf16_tflops_sustained"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(clips_pin.numel() * 4 + noise_pin.numel() * 4),
                     "d2h_bytes_per_step": int(clips_pin.numel() * 4)},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms,
             "clocks": clocks,
             "flops": {"executed_per_step_per_gpu": flops_exec / args.steps,
                       "dense_reference_equivalent_per_step_per_gpu": dense_flops_step,

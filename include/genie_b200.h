@@ -128,10 +128,13 @@ int gn_remask_step(int32_t* prompt_frame, int64_t clip_stride, const int32_t* sa
 int gn_cross_entropy(const float* logits_rows, const int32_t* targets, int R, int V, int NV, const uint8_t* weight,
                      double* acc, void* stream);
 
-/* Live timing of the tcgen05 linear-layer kernel (bench.py roofline leg): between begin and end every
- * tensor-path GEMM launch is bracketed by CUDA events on its stream; out3 = {sum ms, sum 2*M*N*K, launches}. */
+/* Live per-launch timing (bench.py roofline leg): between begin and end every hot-path kernel launch is bracketed
+ * by CUDA events on its stream.  out[2c] = total ms, out[2c+1] = launches of category c, for the
+ * GN_PROF_CATEGORIES categories {gemm store, gemm gelu, gemm residual, prep/LN, spatial attn, temporal attn,
+ * other}; out[2*GN_PROF_CATEGORIES] = sum of 2*M*N*K over the tcgen05 GEMM launches. */
+#define GN_PROF_CATEGORIES 7
 int gn_profile_begin(void);
-int gn_profile_end(double* out3);
+int gn_profile_end(double* out /* 2*GN_PROF_CATEGORIES + 1 doubles */);
 
 /* counters for bench accounting */
 uint64_t gn_kernel_launches(void);              /* kernels launched by this library since load */

@@ -42,12 +42,16 @@ def bench(M, N, K, epi, out_bf16, dual, flush, reps=20):
 
 
 if __name__ == "__main__":
+    only = sys.argv[1] if len(sys.argv) > 1 else None
+    Ms = [int(sys.argv[2])] if len(sys.argv) > 2 else (4096, 16384, 65536, 262144)
     shapes = [("qkv", 1536, 512, 0, True, False), ("proj+res(dual)", 512, 512, 2, False, True),
               ("proj+res", 512, 512, 2, False, False), ("fc1+gelu", 2048, 512, 1, True, False),
               ("fc2+res", 512, 2048, 2, False, False), ("readout", 1024, 512, 0, False, False)]
-    for M in (4096, 16384, 65536, 262144):
+    for M in Ms:
         for name, N, K, epi, obf, dual in shapes:
-            for flush in (False, True):
-                us, tf = bench(M, N, K, epi, obf, dual, flush)
+            if only and only != name:
+                continue
+            for flush in ((False,) if only else (False, True)):
+                us, tf = bench(M, N, K, epi, obf, dual, flush, reps=3 if only else 20)
                 print(json.dumps({"M": M, "name": name, "N": N, "K": K, "l2_flush": flush, "us": round(us, 1),
                                   "tflops": round(tf, 1)}), flush=True)
