@@ -28,6 +28,12 @@ class gn_config(C.Structure):
     ]
 
 
+class gn_vq_config(C.Structure):
+    _fields_ = [("in_channels", C.c_int32), ("z_channels", C.c_int32), ("out_channels", C.c_int32),
+                ("base_channels", C.c_int32), ("num_blocks", C.c_int32), ("ch_mult", C.c_int32 * 8),
+                ("num_res_blocks", C.c_int32)]
+
+
 _vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
 
 # name -> (restype, argtypes); must list every symbol of include/genie_b200.h (checked by tests/test_abi.py)
@@ -50,6 +56,12 @@ SIGNATURES = {
     "gn_sample_tokens": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "gn_remask_step": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "gn_cross_entropy": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "gn_vq_create": (_i, [C.POINTER(_vp), C.POINTER(gn_vq_config), _i]),
+    "gn_vq_destroy": (None, [_vp]),
+    "gn_vq_set_weight": (_i, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i, _vp]),
+    "gn_vq_check_weights": (_i, [_vp, _i, _i]),
+    "gn_vq_encode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "gn_vq_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "gn_profile_begin": (_i, []),
     "gn_profile_end": (_i, [C.POINTER(C.c_double)]),
     "gn_kernel_launches": (C.c_uint64, []),

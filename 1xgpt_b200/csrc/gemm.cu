@@ -50,6 +50,8 @@ struct TcArgs {
   const float* resid;
   int64_t ldr;
   int round_tf32;
+  // implicit-GEMM convolution (cin_blocks == 0: plain GEMM)
+  int cin_blocks, Ho, Wo, tw, th, stride;
 };
 
 template <typename OutT>
@@ -112,7 +114,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int num_m = (args.M + BLOCK_M - 1) / BLOCK_M;
   const int num_n = args.N / BLOCK_N;
   const int num_tiles = num_m * num_n;
-  const int num_kb = (args.K + BLOCK_K - 1) / BLOCK_K;
+  const int num_kb = args.cin_blocks > 0 ? 9 * args.cin_blocks : (args.K + BLOCK_K - 1) / BLOCK_K;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -148,6 +150,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
+          if (args.cin_blocks > 0) {
+            // conv: tile = th x tw output pixels of image n starting at (y0, x0); k-block = (tap, channel block)
+            const int P = args.Ho * args.Wo;
+            const int p0 = m_blk * BLOCK_M;
+            const int n = p0 / P, rem = p0 % P;
+            const int y0 = rem / args.Wo, x0 = rem % args.Wo;
+            const int tap = kb / args.cin_blocks, cib = kb % args.cin_blocks;
+            tma_load_4d(smem_a + stage * A_TILE_BYTES, &tmA, &full_bar[stage], cib * BLOCK_K,
+                        x0 * args.stride + tap % 3 - 1, y0 * args.stride + tap / 3 - 1, n);
+          } else
           tma_load_2d(smem_a + stage * A_TILE_BYTES, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
           tma_load_2d(smem_b + stage * SM::B_TILE_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -358,6 +370,14 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
   const CUtensorMapDataType out_dt =
       sizeof(OutT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUtensorMap tmA, tmB, tmO, tmO2, tmR;
+  int tw = 0, th = 0;
+  if (a.conv) {
+    const ConvGeom& g = *a.conv;
+    tw = g.Wo < BLOCK_M ? g.Wo : BLOCK_M;
+    th = BLOCK_M / tw;
+    GN_PROPAGATE(make_tensor_map_nhwc(&tmA, a.A, in_dt, sizeof(InT), g.Nimg, g.Hi, g.Wi, g.Cin, BLOCK_K, tw, th, g.stride,
+                                      g.stride, CU_TENSOR_MAP_SWIZZLE_128B));
+  } else
   GN_PROPAGATE(make_tensor_map_2d(&tmA, a.A, in_dt, sizeof(InT), a.K, a.M, a.lda, BLOCK_K, BLOCK_M,
                                   CU_TENSOR_MAP_SWIZZLE_128B));
   GN_PROPAGATE(make_tensor_map_2d(&tmB, a.W, in_dt, sizeof(InT), a.K, a.N, a.ldw, BLOCK_K, BLOCK_N,
@@ -389,7 +409,11 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
   if (!cached_sms) cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev);
   sms = cached_sms > 0 ? cached_sms : 148;
   const int grid = num_tiles < sms ? num_tiles : sms;
-  TcArgs t{a.M, a.N, a.K, a.bias, a.resid, a.ldr, a.round_out_tf32};
+  TcArgs t{a.M, a.N, a.K, a.bias, a.resid, a.ldr, a.round_out_tf32, 0, 0, 0, 0, 0, 1};
+  if (a.conv) {
+    t.cin_blocks = a.conv->Cin / BLOCK_K;
+    t.Ho = a.conv->Ho; t.Wo = a.conv->Wo; t.tw = tw; t.th = th; t.stride = a.conv->stride;
+  }
   g_gemm_flops_issued += 2.0 * a.M * (double)a.N * a.K;
   const int cat = EPI == EPI_RESID ? PC_GEMM_RESID : (EPI == EPI_GELU ? PC_GEMM_GELU : PC_GEMM_STORE);
   GN_CUDA_CHECK(launch_kernel(cat, kern, dim3(grid), dim3(GEMM_THREADS), SM::TOTAL, stream, tmA, tmB, tmO, tmO2, tmR, t));
@@ -501,6 +525,19 @@ int linear_forward(const LinearArgs& a, cudaStream_t stream) {
   GN_REQUIRE(a.A && a.W && a.out, "linear_forward: null operand");
   GN_REQUIRE(a.epi != EPI_RESID || a.resid, "linear_forward: EPI_RESID needs a residual pointer");
   const int esz = a.in_bf16 ? 2 : 4;
+  if (a.conv) {
+    const ConvGeom& g = *a.conv;
+    const int bk = 128 / esz;
+    GN_REQUIRE(!a.force_simt, "conv: tensor path only");
+    GN_REQUIRE(g.Cin % bk == 0 && a.K == 9 * g.Cin, "conv: Cin %d must be a multiple of %d and K == 9*Cin", g.Cin, bk);
+    GN_REQUIRE(a.N % 64 == 0, "conv: Cout %d must be a multiple of 64", a.N);
+    GN_REQUIRE(g.stride == 1 || g.stride == 2, "conv: stride must be 1 or 2");
+    GN_REQUIRE(a.M == g.Nimg * g.Ho * g.Wo, "conv: M != Nimg*Ho*Wo");
+    GN_REQUIRE((g.Ho * g.Wo) % 128 == 0 && (g.Wo >= 128 ? g.Wo % 128 == 0 : 128 % g.Wo == 0),
+               "conv: output %dx%d not tileable by 128-pixel tiles", g.Ho, g.Wo);
+    GN_REQUIRE(g.Wo >= 128 || g.Ho % (128 / g.Wo) == 0, "conv: Ho not a multiple of the tile height");
+    GN_REQUIRE((g.Wo < 128 ? g.Wo : 128) * g.stride <= 256, "conv: TMA box too wide");
+  }
   const bool tc_ok = !a.force_simt && (a.N % 64 == 0) && (a.K * esz % 16 == 0) && (a.lda * esz % 16 == 0) &&
                      (a.ldw * esz % 16 == 0) && (a.ldo * (a.out_bf16 ? 2 : 4) % 16 == 0) &&
                      (!a.out2 || a.ldo2 * 2 % 16 == 0) && (!a.resid || a.ldr * 4 % 16 == 0) &&

@@ -16,6 +16,16 @@ namespace gn {
 
 enum EpiKind : int { EPI_STORE = 0, EPI_GELU = 1, EPI_RESID = 2 };
 
+// Implicit-GEMM 3x3 convolution (padding 1, stride 1 or 2) on the same kernel: A is the NHWC bf16 input
+// [Nimg, Hi, Wi, Cin]; the K loop runs over (tap, 64-channel block) and the A tile of a k-block is the TMA box of
+// the 128 output pixels of the tile shifted by the tap (out-of-bounds = zero padding).  W is [Cout, 9*Cin]
+// (tap-major).  Output rows are flat NHWC output pixels.
+struct ConvGeom {
+  int Nimg, Hi, Wi, Cin;   // input
+  int Ho, Wo;              // output spatial size
+  int stride;              // 1 or 2
+};
+
 struct LinearArgs {
   const void* A;      // [M, lda]  bf16 or f32
   int64_t lda;
@@ -34,6 +44,7 @@ struct LinearArgs {
   int out_bf16;       // 1: out is bf16, 0: f32
   int force_simt;     // 1: CUDA-core fp32 path regardless of shape
   int round_out_tf32; // 1: round the fp32 output to tf32 (it feeds a kind::tf32 GEMM next)
+  const ConvGeom* conv; // non-null: implicit-GEMM 3x3 convolution (A = NHWC input, K = 9*Cin, M = Nimg*Ho*Wo)
 };
 
 // Enqueue on `stream`.  Returns GN_OK or a negative code (message via last_error()).

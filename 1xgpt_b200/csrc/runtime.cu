@@ -85,13 +85,16 @@ static EncodeTiledFn get_encode() {
 }
 
 static int encode(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int rank, const cuuint64_t* dims,
-                  const cuuint64_t* strides_bytes, const cuuint32_t* box, CUtensorMapSwizzle swz) {
+                  const cuuint64_t* strides_bytes, const cuuint32_t* box, CUtensorMapSwizzle swz,
+                  const cuuint32_t* elem_strides = nullptr) {
   EncodeTiledFn fn = get_encode();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
     return GN_ERR_CUDA;
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (elem_strides)
+    for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
   CUresult r = fn(out, dt, rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -118,6 +121,16 @@ int make_tensor_map_3d(CUtensorMap* out, const void* base, CUtensorMapDataType d
   cuuint64_t strides[2] = {(cuuint64_t)stride1 * elem_bytes, (cuuint64_t)stride2 * elem_bytes};
   cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, (cuuint32_t)box2};
   return encode(out, base, dt, 3, dims, strides, box, swz);
+}
+
+int make_tensor_map_nhwc(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int elem_bytes, int64_t N,
+                         int64_t H, int64_t W, int64_t C, int box_c, int box_w, int box_h, int stride_w, int stride_h,
+                         CUtensorMapSwizzle swz) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * elem_bytes, (cuuint64_t)W * C * elem_bytes, (cuuint64_t)H * W * C * elem_bytes};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * stride_w), (cuuint32_t)(box_h * stride_h), 1};
+  cuuint32_t es[4] = {1, (cuuint32_t)stride_w, (cuuint32_t)stride_h, 1};
+  return encode(out, base, dt, 4, dims, strides, box, swz, es);
 }
 
 }  // namespace gn

@@ -14,4 +14,11 @@ int make_tensor_map_3d(CUtensorMap* out, const void* base, CUtensorMapDataType d
                        int64_t d1, int64_t d2, int64_t stride1, int64_t stride2, int box0, int box1, int box2,
                        CUtensorMapSwizzle swz);
 
+// 4-D NHWC activation tensor [N, H, W, C] (C innermost) for implicit-GEMM convolution: box {bc, bw, bh, 1} in
+// traversal elements with per-dimension traversal strides (1, sw, sh, 1); out-of-bounds coordinates read zeros,
+// which implements the conv padding.
+int make_tensor_map_nhwc(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int elem_bytes, int64_t N,
+                         int64_t H, int64_t W, int64_t C, int box_c, int box_w, int box_h, int stride_w, int stride_h,
+                         CUtensorMapSwizzle swz);
+
 }  // namespace gn

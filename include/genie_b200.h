@@ -136,6 +136,35 @@ int gn_cross_entropy(const float* logits_rows, const int32_t* targets, int R, in
 int gn_profile_begin(void);
 int gn_profile_end(double* out /* 2*GN_PROF_CATEGORIES + 1 doubles */);
 
+/* ------------------------------------------------------------------ MAGVIT2 tokenizer (second kernel family)
+ * Encoder -> LFQ -> tokens and tokens -> LFQ^-1 -> Decoder.
+ * reference: magvit2/modules/diffusionmodules/improved_model.py:54-182, lookup_free_quantize.py:181-194,241-257,
+ * magvit2/models/lfqgan.py:121-129 (VQModel.encode/decode), visualize.py:84-116 (decode wrapper). */
+typedef struct gn_vq gn_vq;
+typedef struct gn_vq_config { /* mirrors magvit2/config.py:12-18 (VQConfig) */
+  int32_t in_channels;    /* 3 */
+  int32_t z_channels;     /* 18 */
+  int32_t out_channels;   /* 3 */
+  int32_t base_channels;  /* 128 */
+  int32_t num_blocks;     /* len(ch_mult) = 5 */
+  int32_t ch_mult[8];     /* (1, 1, 2, 2, 4) */
+  int32_t num_res_blocks; /* 2 */
+} gn_vq_config;
+int gn_vq_create(gn_vq** out, const gn_vq_config* cfg, int device);
+void gn_vq_destroy(gn_vq* m);
+/* keys of VQModel.state_dict(): "encoder.conv_in.weight", "encoder.down.0.block.0.norm1.weight", ...,
+ * "decoder.up.4.upsample.conv1.weight", ...; src is fp32 on the device in PyTorch layout (OIHW for convs). */
+int gn_vq_set_weight(gn_vq* m, const char* key, const float* src, const int64_t* shape, int ndim, void* stream);
+int gn_vq_check_weights(gn_vq* m, int need_encoder, int need_decoder);
+/* img [B,3,H,W] fp32 in [-1,1] -> ids [B, (H/16)*(W/16)] (big-endian LFQ index, lookup_free_quantize.py:257);
+ * z_out [B, z_channels, H/16, W/16] (pre-quantisation latents, nullable). */
+int gn_vq_encode(gn_vq* m, const float* img, int B, int H, int W, int32_t* ids, float* z_out, void* stream);
+/* ids [B, h*w] -> img_f32 [B,3,16h,16w] (decoder output, nullable) and/or img_u8 ((v+1)*127.5 clamped, nullable).
+ * little_endian=1 reproduces visualize.py:111-116 (get_codebook_entry(...).flip(1): dataset tokens store bit c in
+ * latent channel c); little_endian=0 inverts gn_vq_encode's own indices. */
+int gn_vq_decode(gn_vq* m, const int32_t* ids, int B, int h, int w, int little_endian, float* img_f32, uint8_t* img_u8,
+                 void* stream);
+
 /* counters for bench accounting */
 uint64_t gn_kernel_launches(void);              /* kernels launched by this library since load */
 double gn_model_flops_per_clip_forward(gn_model* m); /* dense reference-equivalent FLOPs */

@@ -183,3 +183,42 @@ if __name__ == "__main__":
     production("genie35m", kw35, B=2, seed=21)
     production("genie138m", dict(kw35, d_model=512), B=1, seed=22)
     production("genie138m_qknorm_mup", dict(kw35, d_model=512, qk_norm=True, use_mup=True), B=1, seed=23)
+
+
+@torch.no_grad()
+def magvit_fixture():
+    """MAGVIT2 Encoder / LFQ / Decoder of the reference on synthetic weights and images (these
+    modules import stand-alone; `lightning` is only needed by VQModel)."""
+    from oracle import magvit_oracle as MO
+    sys.path.insert(0, "/root/reference")
+    from magvit2.config import VQConfig
+    from magvit2.modules.diffusionmodules.improved_model import Encoder, Decoder
+    from magvit2.modules.vqvae.lookup_free_quantize import LFQ
+    cfg = MO.VQOracleConfig()
+    sd = MO.init_vq_state_dict(cfg, seed=31)
+    vq = VQConfig()
+    enc, dec, lfq = Encoder(vq).eval(), Decoder(vq).eval(), LFQ(vq).eval()
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}, strict=True)
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}, strict=True)
+    g = torch.Generator().manual_seed(7)
+    img = torch.rand(2, 3, 256, 256, generator=g) * 2 - 1
+    z = enc(img)                                                   # [2,18,16,16]
+    (quant, _, idx), _ = lfq(z, return_loss_breakdown=True)
+    idx = idx.reshape(2, 16, 16)
+    rec = dec(quant)                                               # VQModel.decode(quant)
+    # dataset-style decode (visualize.py:111-116): little-endian tokens
+    tok = torch.randint(0, 2 ** 18, (1, 16, 16), generator=g)
+    q_le = lfq.get_codebook_entry(tok.reshape(1, -1), bhwc=(1, 16, 16, 18)).flip(1)
+    img_le = dec(q_le)
+    np.savez_compressed(
+        os.path.join(OUT, "magvit.npz"), seed=np.int64(31), sd_sha=np.array(sd_sha(sd)), img_seed=np.int64(7),
+        z=z.numpy(), ids=idx.numpy().astype(np.int32), quant_sign=(quant > 0).numpy(),
+        rec_sub=rec[:, :, ::8, ::8].numpy(), rec_absmax=np.float32(rec.abs().max()),
+        rec_fro=np.float64(torch.linalg.vector_norm(rec.double())),
+        tok_le=tok.numpy().astype(np.int32), img_le_sub=img_le[:, :, ::8, ::8].numpy(),
+        img_le_fro=np.float64(torch.linalg.vector_norm(img_le.double())))
+    print("magvit ok", float(z.abs().mean()), float(rec.abs().max()))
+
+
+if __name__ == "__main__" and os.environ.get("GOLDEN_MAGVIT", "1") == "1":
+    magvit_fixture()
