@@ -249,154 +249,182 @@ int launch_spatial_t(const AttnArgs& a, int n_frames, int S, cudaStream_t st) {
 }
 
 // =====================================================================================
-// temporal attention: one CTA per (clip, spatial position), one warp per head
+// temporal attention: persistent CTAs, one warp per head, looping over (clip, spatial position) with a 2-stage
+// cp.async ring: the K/V rows (cache + fresh) of position i+1 stream into shared memory while position i is
+// computed, so the kernel is a continuous HBM stream (it is bandwidth-bound: (t0+Tq)*2*d*2 B of K/V per token).
 // =====================================================================================
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = smem_u32(smem_dst);
+  const int sz = valid ? 16 : 0;   // src-size 0 -> the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int HD>
 __global__ void __launch_bounds__(512)
 temporal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, bf16* __restrict__ kcache,
-                     bf16* __restrict__ vcache, int S, int T, int t0, int Tq, int d, float scale_log2e,
+                     bf16* __restrict__ vcache, int n_pos, int S, int T, int t0, int Tq, int d, float scale_log2e,
                      const float* __restrict__ gamma, const float* __restrict__ beta) {
   constexpr int ROWB = HD * 2;
   constexpr int CH = HD / 8;
   constexpr int TILEB = 16 * ROWB;
+  constexpr int NIT = 16 * CH / 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = warp;
-  const int b = blockIdx.x / S, sp = blockIdx.x % S;
-  uint8_t* sQ = smem + warp * 3 * TILEB;
-  uint8_t* sK = sQ + TILEB;
-  uint8_t* sV = sK + TILEB;
+  uint8_t* wbase = smem + warp * 2 * 3 * TILEB;     // [stage][q|k|v]
   const int Tk = t0 + Tq;
-  pdl_wait();
-  pdl_trigger();
-  const int64_t fresh0 = ((int64_t)b * Tq) * S + sp;     // fresh row of local frame tl: fresh0 + tl*S
-  const int64_t cache0 = ((int64_t)b * S + sp) * T;      // cache row of frame j: cache0 + j  ([B,S,T,d]: the
-                                                         // frames of one position are contiguous)
-
-  // Phase 1: issue EVERY global load of this warp (q, k, v rows of up to 16 frames) before the first store, so the
-  // whole tile is one round trip to HBM/L2 instead of one per unrolled iteration (the cache update below
-  // aliases kcache/vcache from the compiler's point of view and would otherwise serialise the iterations).
-  constexpr int NIT = 16 * CH / 32;
-  uint4 qv[NIT], kv[NIT], vv[NIT];
-#pragma unroll
-  for (int it = 0; it < NIT; ++it) {
-    const int idx = it * 32 + lane;
-    const int r = idx / CH, c = idx % CH;
-    qv[it] = make_uint4(0, 0, 0, 0);
-    kv[it] = qv[it];
-    vv[it] = qv[it];
-    if (r < Tq) qv[it] = __ldg(reinterpret_cast<const uint4*>(qkv + (fresh0 + (int64_t)r * S) * 3 * d + h * HD + c * 8));
-    if (r < Tk) {
-      if (r < t0) {
-        const int64_t cr = (cache0 + r) * d + h * HD + c * 8;
-        kv[it] = *reinterpret_cast<const uint4*>(kcache + cr);
-        vv[it] = *reinterpret_cast<const uint4*>(vcache + cr);
-      } else {
-        const int64_t fr = (fresh0 + (int64_t)(r - t0) * S) * 3 * d + h * HD + c * 8;
-        kv[it] = __ldg(reinterpret_cast<const uint4*>(qkv + fr + d));
-        vv[it] = __ldg(reinterpret_cast<const uint4*>(qkv + fr + 2 * d));
-      }
-    }
-  }
-  // Phase 2: stage in shared memory, append the fresh frames to the K/V cache
-#pragma unroll
-  for (int it = 0; it < NIT; ++it) {
-    const int idx = it * 32 + lane;
-    const int r = idx / CH, c = idx % CH;
-    if (kcache != nullptr && r >= t0 && r < Tk) {
-      const int64_t cr = (cache0 + r) * d + h * HD + c * 8;
-      *reinterpret_cast<uint4*>(kcache + cr) = kv[it];
-      *reinterpret_cast<uint4*>(vcache + cr) = vv[it];
-    }
-    *reinterpret_cast<uint4*>(sQ + swz<HD>(r, c)) = qv[it];
-    *reinterpret_cast<uint4*>(sK + swz<HD>(r, c)) = kv[it];
-    *reinterpret_cast<uint4*>(sV + swz<HD>(r, c)) = vv[it];
-  }
-  __syncwarp();
-  if (gamma != nullptr) {
-    qk_layernorm_rows<HD>(sQ, Tq, lane, 32, gamma, beta);
-    qk_layernorm_rows<HD>(sK, Tk, lane, 32, gamma, beta);
-    __syncwarp();
-  }
-  const uint32_t sQa = smem_u32(sQ), sKa = smem_u32(sK), sVa = smem_u32(sV);
   const int mi = lane >> 3, l8 = lane & 7;
   const int g = lane >> 2, t4 = lane & 3;
+  pdl_wait();
+  pdl_trigger();
 
-  float s[2][4];
-  s[0][0] = s[0][1] = s[0][2] = s[0][3] = 0.f;
-  s[1][0] = s[1][1] = s[1][2] = s[1][3] = 0.f;
+  auto prefetch = [&](int pos, int stage) {
+    const int b = pos / S, sp = pos % S;
+    const int64_t fresh0 = ((int64_t)b * Tq) * S + sp;     // fresh row of local frame tl: fresh0 + tl*S
+    const int64_t cache0 = ((int64_t)b * S + sp) * T;      // cache row of frame j (layout [B,S,T,d])
+    uint8_t* sQ = wbase + stage * 3 * TILEB;
+    uint8_t* sK = sQ + TILEB;
+    uint8_t* sV = sK + TILEB;
 #pragma unroll
-  for (int kk = 0; kk < HD / 16; ++kk) {
-    uint32_t qf[4], kf[4];
-    ldsm_x4(qf, sQa + swz<HD>(l8 + (mi & 1) * 8, 2 * kk + (mi >> 1)));
-    ldsm_x4(kf, sKa + swz<HD>((mi >> 1) * 8 + l8, 2 * kk + (mi & 1)));
-    mma_16816(s[0], qf, kf[0], kf[1]);
-    mma_16816(s[1], qf, kf[2], kf[3]);
-  }
-  // causal mask: query row i (frame t0 + i) sees keys j <= t0 + i   (attention.py:51-55)
-  float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int key = j * 8 + 2 * t4 + e;
-      if (key > t0 + g) s[j][e] = -INFINITY;
-      if (key > t0 + g + 8) s[j][2 + e] = -INFINITY;
-      mx0 = fmaxf(mx0, s[j][e]);
-      mx1 = fmaxf(mx1, s[j][2 + e]);
+    for (int it = 0; it < NIT; ++it) {
+      const int idx = it * 32 + lane;
+      const int r = idx / CH, c = idx % CH;
+      const bf16* qsrc = qkv + (fresh0 + (int64_t)(r < Tq ? r : 0) * S) * 3 * d + h * HD + c * 8;
+      cp_async16(sQ + swz<HD>(r, c), qsrc, r < Tq);
+      const bf16 *ksrc, *vsrc;
+      if (r < t0) {
+        const int64_t cr = (cache0 + r) * d + h * HD + c * 8;
+        ksrc = kcache + cr;
+        vsrc = vcache + cr;
+      } else {
+        const int64_t fr = (fresh0 + (int64_t)(r < Tk ? r - t0 : 0) * S) * 3 * d + h * HD + c * 8;
+        ksrc = qkv + fr + d;
+        vsrc = qkv + fr + 2 * d;
+      }
+      cp_async16(sK + swz<HD>(r, c), ksrc, r < Tk);
+      cp_async16(sV + swz<HD>(r, c), vsrc, r < Tk);
     }
-  }
-  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-  float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      s[j][e] = exp2f((s[j][e] - mx0) * scale_log2e);
-      s[j][2 + e] = exp2f((s[j][2 + e] - mx1) * scale_log2e);
-      l0 += s[j][e];
-      l1 += s[j][2 + e];
+    cp_async_commit();
+  };
+
+  int pos = blockIdx.x;
+  int stage = 0;
+  if (pos < n_pos) prefetch(pos, 0);
+  for (; pos < n_pos; pos += gridDim.x, stage ^= 1) {
+    const int nxt = pos + gridDim.x;
+    if (nxt < n_pos) {
+      prefetch(nxt, stage ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float i0 = 1.f / l0, i1 = 1.f / l1;
-  uint32_t pa[4];
-  pa[0] = pack_bf16x2(s[0][0], s[0][1]);
-  pa[1] = pack_bf16x2(s[0][2], s[0][3]);
-  pa[2] = pack_bf16x2(s[1][0], s[1][1]);
-  pa[3] = pack_bf16x2(s[1][2], s[1][3]);
-  float o[HD / 8][4];
+    __syncwarp();
+    const int b = pos / S, sp = pos % S;
+    const int64_t fresh0 = ((int64_t)b * Tq) * S + sp;
+    const int64_t cache0 = ((int64_t)b * S + sp) * T;
+    uint8_t* sQ = wbase + stage * 3 * TILEB;
+    uint8_t* sK = sQ + TILEB;
+    uint8_t* sV = sK + TILEB;
+    // append the fresh frames (raw projections) to the K/V cache
+    if (kcache != nullptr) {
 #pragma unroll
-  for (int jp = 0; jp < HD / 16; ++jp) {
-    uint32_t vf[4];
-    ldsm_x4_t(vf, sVa + swz<HD>((mi & 1) * 8 + l8, 2 * jp + (mi >> 1)));
-    o[2 * jp][0] = o[2 * jp][1] = o[2 * jp][2] = o[2 * jp][3] = 0.f;
-    o[2 * jp + 1][0] = o[2 * jp + 1][1] = o[2 * jp + 1][2] = o[2 * jp + 1][3] = 0.f;
-    mma_16816(o[2 * jp], pa, vf[0], vf[1]);
-    mma_16816(o[2 * jp + 1], pa, vf[2], vf[3]);
-  }
-  __syncwarp();
-#pragma unroll
-  for (int j = 0; j < HD / 8; ++j) {
-    *reinterpret_cast<uint32_t*>(sQ + swz<HD>(g, j) + t4 * 4) = pack_bf16x2(o[j][0] * i0, o[j][1] * i0);
-    *reinterpret_cast<uint32_t*>(sQ + swz<HD>(g + 8, j) + t4 * 4) = pack_bf16x2(o[j][2] * i1, o[j][3] * i1);
-  }
-  __syncwarp();
-#pragma unroll
-  for (int it = 0; it < 16 * CH / 32; ++it) {
-    const int idx = it * 32 + lane;
-    const int r = idx / CH, c = idx % CH;
-    if (r < Tq) {
-      const uint4 v = *reinterpret_cast<const uint4*>(sQ + swz<HD>(r, c));
-      *reinterpret_cast<uint4*>(out + (fresh0 + (int64_t)r * S) * d + h * HD + c * 8) = v;
+      for (int it = 0; it < NIT; ++it) {
+        const int idx = it * 32 + lane;
+        const int r = idx / CH, c = idx % CH;
+        if (r >= t0 && r < Tk) {
+          const int64_t cr = (cache0 + r) * d + h * HD + c * 8;
+          *reinterpret_cast<uint4*>(kcache + cr) = *reinterpret_cast<const uint4*>(sK + swz<HD>(r, c));
+          *reinterpret_cast<uint4*>(vcache + cr) = *reinterpret_cast<const uint4*>(sV + swz<HD>(r, c));
+        }
+      }
     }
+    if (gamma != nullptr) {
+      qk_layernorm_rows<HD>(sQ, Tq, lane, 32, gamma, beta);
+      qk_layernorm_rows<HD>(sK, Tk, lane, 32, gamma, beta);
+      __syncwarp();
+    }
+    const uint32_t sQa = smem_u32(sQ), sKa = smem_u32(sK), sVa = smem_u32(sV);
+
+    float s[2][4];
+    s[0][0] = s[0][1] = s[0][2] = s[0][3] = 0.f;
+    s[1][0] = s[1][1] = s[1][2] = s[1][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) {
+      uint32_t qf[4], kf[4];
+      ldsm_x4(qf, sQa + swz<HD>(l8 + (mi & 1) * 8, 2 * kk + (mi >> 1)));
+      ldsm_x4(kf, sKa + swz<HD>((mi >> 1) * 8 + l8, 2 * kk + (mi & 1)));
+      mma_16816(s[0], qf, kf[0], kf[1]);
+      mma_16816(s[1], qf, kf[2], kf[3]);
+    }
+    // causal mask: query row i (frame t0 + i) sees keys j <= t0 + i   (attention.py:51-55)
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int key = j * 8 + 2 * t4 + e;
+        if (key > t0 + g) s[j][e] = -INFINITY;
+        if (key > t0 + g + 8) s[j][2 + e] = -INFINITY;
+        mx0 = fmaxf(mx0, s[j][e]);
+        mx1 = fmaxf(mx1, s[j][2 + e]);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        s[j][e] = exp2f((s[j][e] - mx0) * scale_log2e);
+        s[j][2 + e] = exp2f((s[j][2 + e] - mx1) * scale_log2e);
+        l0 += s[j][e];
+        l1 += s[j][2 + e];
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    uint32_t pa[4];
+    pa[0] = pack_bf16x2(s[0][0], s[0][1]);
+    pa[1] = pack_bf16x2(s[0][2], s[0][3]);
+    pa[2] = pack_bf16x2(s[1][0], s[1][1]);
+    pa[3] = pack_bf16x2(s[1][2], s[1][3]);
+    float o[HD / 8][4];
+#pragma unroll
+    for (int jp = 0; jp < HD / 16; ++jp) {
+      uint32_t vf[4];
+      ldsm_x4_t(vf, sVa + swz<HD>((mi & 1) * 8 + l8, 2 * jp + (mi >> 1)));
+      o[2 * jp][0] = o[2 * jp][1] = o[2 * jp][2] = o[2 * jp][3] = 0.f;
+      o[2 * jp + 1][0] = o[2 * jp + 1][1] = o[2 * jp + 1][2] = o[2 * jp + 1][3] = 0.f;
+      mma_16816(o[2 * jp], pa, vf[0], vf[1]);
+      mma_16816(o[2 * jp + 1], pa, vf[2], vf[3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < HD / 8; ++j) {
+      *reinterpret_cast<uint32_t*>(sQ + swz<HD>(g, j) + t4 * 4) = pack_bf16x2(o[j][0] * i0, o[j][1] * i0);
+      *reinterpret_cast<uint32_t*>(sQ + swz<HD>(g + 8, j) + t4 * 4) = pack_bf16x2(o[j][2] * i1, o[j][3] * i1);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int idx = it * 32 + lane;
+      const int r = idx / CH, c = idx % CH;
+      if (r < Tq) {
+        const uint4 v = *reinterpret_cast<const uint4*>(sQ + swz<HD>(r, c));
+        *reinterpret_cast<uint4*>(out + (fresh0 + (int64_t)r * S) * d + h * HD + c * 8) = v;
+      }
+    }
+    __syncwarp();   // this stage is refilled two iterations from now
   }
 }
 
@@ -404,17 +432,27 @@ template <int HD>
 int launch_temporal_t(const AttnArgs& a, int B, int S, int T, int t0, int Tq, void* kcache, void* vcache,
                       cudaStream_t st) {
   const int d = a.n_heads * a.head_dim;
-  const int smem = a.n_heads * 3 * 16 * HD * 2 + 1024;
+  const int smem = a.n_heads * 2 * 3 * 16 * HD * 2 + 1024;
   auto kern = temporal_attn_kernel<HD>;
   static int set = 0;
   if (smem > 48 * 1024 && smem > set) {
     GN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     set = smem;
   }
-  GN_CUDA_CHECK(launch_kernel(PC_TEMPORAL, kern, dim3(B * S), dim3(a.n_heads * 32), (size_t)smem, st,
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int per_sm = std::max(1, (227 * 1024) / smem);
+  const int n_pos = B * S;
+  const int grid = std::min(n_pos, sms * per_sm);
+  GN_CUDA_CHECK(launch_kernel(PC_TEMPORAL, kern, dim3(grid), dim3(a.n_heads * 32), (size_t)smem, st,
                               static_cast<const bf16*>(a.qkv), static_cast<bf16*>(a.out), static_cast<bf16*>(kcache),
-                              static_cast<bf16*>(vcache), S, T, t0, Tq, d, a.scale * 1.4426950408889634f, a.qk_gamma,
-                              a.qk_beta));
+                              static_cast<bf16*>(vcache), n_pos, S, T, t0, Tq, d, a.scale * 1.4426950408889634f,
+                              a.qk_gamma, a.qk_beta));
   ++g_launch_count;
   return GN_OK;
 }

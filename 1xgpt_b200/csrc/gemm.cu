@@ -437,8 +437,8 @@ int dispatch_epi(const LinearArgs& a, cudaStream_t s) {
       return a.out2 ? launch_tc<InT, BLOCK_N, EPI_RESID, float, true>(a, s)
                     : launch_tc<InT, BLOCK_N, EPI_RESID, float, false>(a, s);
     } else {
-      set_error("EPI_RESID is tiled with BLOCK_N <= 128");
-      return GN_ERR_INVALID;
+      if (a.out2) { set_error("EPI_RESID with a bf16 copy is tiled with BLOCK_N <= 128"); return GN_ERR_INVALID; }
+      return launch_tc<InT, BLOCK_N, EPI_RESID, float, false>(a, s);
     }
   }
   set_error("unknown epilogue %d", a.epi);
@@ -447,9 +447,11 @@ int dispatch_epi(const LinearArgs& a, cudaStream_t s) {
 
 template <typename InT>
 int dispatch_n(const LinearArgs& a, cudaStream_t s) {
-  // BLOCK_N = 256 keeps the smem operand traffic per MMA cycle under the 128 B/clk port limit; the
-  // residual epilogues (fp32 + optional bf16 copy staging) take 128 to keep a deep TMA ring.
-  if (a.N % 256 == 0 && a.epi != EPI_RESID) return dispatch_epi<InT, 256>(a, s);
+  // BLOCK_N = 256 keeps the smem operand traffic per MMA cycle under the 128 B/clk port limit.
+  // Residual epilogues stage 4 fp32 buffers per warp, so they normally take BLOCK_N = 128 to keep a deep TMA ring;
+  // for long-K residual GEMMs (fc2: K = 4d) the 128-wide tile is operand-bandwidth bound (A+B = 128 B/clk of smem
+  // reads per MMA cycle), so those use 256 with a 3-stage ring.
+  if (a.N % 256 == 0 && (a.epi != EPI_RESID || (a.K >= 1024 && !a.out2))) return dispatch_epi<InT, 256>(a, s);
   if (a.N % 128 == 0) return dispatch_epi<InT, 128>(a, s);
   return dispatch_epi<InT, 64>(a, s);
 }

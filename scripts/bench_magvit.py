@@ -1,0 +1,44 @@
+#!/usr/bin/env python3
+"""MAGVIT2 encode -> 16x16 LFQ tokens -> decode throughput on one GPU (BASELINE.json configs[4], per-GPU share:
+64 synthetic 256x256 frames).  FLOPs per image from SURVEY.md 8d: encoder 135.8 GFLOP, decoder 186.7 GFLOP."""
+import importlib
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import magvit_oracle as MO  # weights only (seeded init)
+
+pkg = importlib.import_module("1xgpt_b200")
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+m = pkg.VQModel()
+m.load_state_dict(MO.init_vq_state_dict(MO.VQOracleConfig(), seed=31))
+m = m.to("cuda")
+img = (torch.rand(B, 3, 256, 256, generator=torch.Generator().manual_seed(7)) * 2 - 1).cuda()
+
+
+def timed(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, out
+
+
+ms_e, ids = timed(lambda: m.encode_to_tokens(img))
+ms_d, _ = timed(lambda: m.decode_tokens(ids, little_endian=False, as_uint8=True))
+peaks = json.load(open("MEASURED_PEAKS.json")) if os.path.exists("MEASURED_PEAKS.json") else {"bf16_tflops_sustained": 1400.0}
+pk = peaks["bf16_tflops_sustained"]
+print(json.dumps({
+    "workload": f"MAGVIT2 encode->16x16 LFQ->decode, {B} synthetic 256x256 frames on 1 GPU, bf16 operands",
+    "encode_ms": ms_e, "encode_img_s": B / ms_e * 1e3, "encode_tflops": B * 135.8e9 / (ms_e * 1e-3) / 1e12,
+    "decode_ms": ms_d, "decode_img_s": B / ms_d * 1e3, "decode_tflops": B * 186.7e9 / (ms_d * 1e-3) / 1e12,
+    "roundtrip_img_s": B / (ms_e + ms_d) * 1e3, "peak_tflops": pk,
+    "encode_frac": B * 135.8e9 / (ms_e * 1e-3) / 1e12 / pk, "decode_frac": B * 186.7e9 / (ms_d * 1e-3) / 1e12 / pk}))

@@ -211,3 +211,29 @@ def test_error_behaviour_matches_reference():
     assert torch.equal(bad, before)                    # untouched on failure
     with pytest.raises(NotImplementedError, match="unmask_mode"):
         m.maskgit_generate(prompt.clone(), 2, unmask_mode="bogus")
+
+
+@pytest.mark.parametrize("qk_norm,use_mup", [(False, False), (True, True)])
+def test_wide_model_shapes_d1024_h16(qk_norm, use_mup):
+    """BASELINE config 4 shape family (d=1024, h=16, hd=64; 2 layers here so the CPU oracle stays fast)."""
+    kw = dict(num_layers=2, num_heads=16, d_model=1024, T=16, S=256, image_vocab_size=262144, num_factored_vocabs=2,
+              qk_norm=qk_norm, use_mup=use_mup)
+    cfg = O.OracleConfig(**kw)
+    sd = O.init_state_dict(cfg, seed=41, bias_std=0.02)
+    ids = O.synthetic_clips(cfg, 1, seed=42)
+    ids[:, 12:] = cfg.mask_token_id
+    ref = O.compute_logits(sd, cfg, ids)
+    for precision in ("bf16", "tf32"):
+        m = build_b200_model(kw, sd, precision=precision)
+        err = rel_fro(m.compute_logits(ids.cuda()), ref)
+        print(f"d1024 h16 qk_norm={qk_norm} {precision}: rel {err:.3e}")
+        assert err < TOL[precision]
+    # 8-step MaskGIT through the cached path == dense path (bit-identical tokens)
+    noise = O.tie_free_noise(8, 1, cfg.S, seed=43)
+    outs = []
+    for kv in (False, True):
+        m = build_b200_model(kw, sd, precision="bf16", kv_cache=kv)
+        p = ids.clone().cuda()
+        s, _ = m.maskgit_generate(p, 12, maskgit_steps=8, temperature=0.0, noise=noise)
+        outs.append(s.cpu())
+    assert torch.equal(outs[0], outs[1])
