@@ -160,6 +160,67 @@ int launch_prep(const float* x, void* out, int out_bf16, const float* gamma, con
   return launch_prep_t<float>(x, static_cast<float*>(out), gamma, beta, n_rows, d, scale, S, Tact, tsel, st, round_tf32);
 }
 
+// bf16 cast + row statistics (feeds the folded-LayerNorm GEMM epilogue of the first layer)
+__global__ void __launch_bounds__(256)
+prep_stats_kernel(const float* __restrict__ x, bf16* __restrict__ out, float* __restrict__ stats, int n_rows, int d) {
+  pdl_wait();
+  pdl_trigger();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* x4 = reinterpret_cast<const float4*>(x + (int64_t)row * d);
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane; c < d / 4; c += 32) {
+    const float4 v = x4[c];
+    s1 += (v.x + v.y) + (v.z + v.w);
+    s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    uint2 p;
+    p.x = pack_bf16x2(v.x, v.y);
+    p.y = pack_bf16x2(v.z, v.w);
+    reinterpret_cast<uint2*>(out + (int64_t)row * d)[c] = p;
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) reinterpret_cast<float2*>(stats)[row] = make_float2(s1, s2);
+}
+int launch_prep_stats(const float* x, bf16* out, float* stats, int n_rows, int d, cudaStream_t st) {
+  GN_REQUIRE(d % 4 == 0, "prep: d_model must be a multiple of 4");
+  GN_CUDA_CHECK(launch_kernel(PC_PREP, prep_stats_kernel, dim3(ceil_div(n_rows, 8)), dim3(256), 0, st, x, out, stats,
+                              n_rows, d));
+  ++g_launch_count;
+  return GN_OK;
+}
+
+// LayerNorm folding, one warp per output feature n
+__global__ void __launch_bounds__(256)
+fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ gamma, const float* __restrict__ beta,
+               const float* __restrict__ bias, bf16* __restrict__ Wf, float* __restrict__ colsum,
+               float* __restrict__ bias_f, int N, int K) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int lane = threadIdx.x & 31;
+  float cs = 0.f, bs = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = W[(int64_t)n * K + k];
+    const bf16 wf = __float2bfloat16_rn(w * gamma[k]);
+    Wf[(int64_t)n * K + k] = wf;
+    cs += __bfloat162float(wf);          // the sum the tensor core will see (mean subtraction stays exact)
+    bs = fmaf(beta[k], w, bs);
+  }
+  cs = warp_sum(cs);
+  bs = warp_sum(bs);
+  if (lane == 0) {
+    colsum[n] = cs;
+    bias_f[n] = bs + (bias ? bias[n] : 0.f);
+  }
+}
+int launch_fold_ln(const float* W, const float* gamma, const float* beta, const float* bias, bf16* Wf, float* colsum,
+                   float* bias_f, int N, int K, cudaStream_t st) {
+  fold_ln_kernel<<<ceil_div(N, 8), 256, 0, st>>>(W, gamma, beta, bias, Wf, colsum, bias_f, N, K);
+  GN_CUDA_CHECK(cudaGetLastError());
+  return GN_OK;
+}
+
 // -------------------------------------------------------------------------------------
 // fp32 -> bf16 weight conversion (weights are repacked once at load time)
 // -------------------------------------------------------------------------------------

@@ -20,8 +20,12 @@ constexpr int TILE_K_BYTES = 128;            // one 128B swizzle atom along K pe
 constexpr int A_TILE_BYTES = BLOCK_M * TILE_K_BYTES;
 constexpr int NUM_ACC_STAGES = 2;
 constexpr int EPI_COLS = 32;                 // accumulator columns handled per epilogue step
-constexpr int NUM_EPI_WARPS = 4;
-constexpr int GEMM_THREADS = 32 * (2 + NUM_EPI_WARPS);
+// Epilogue warps: 4 (one per TMEM lane quarter) for the residual epilogue; 8 (two per quarter, each taking half of the
+// tile's columns) for the store / GELU epilogues, whose per-chunk dependency chain (tcgen05.ld -> math -> staging ->
+// TMA store) is latency bound with a single warp per SM sub-partition.
+template <int EPI> struct EpiCfg { static constexpr int WARPS = EPI == EPI_RESID ? 4 : 8; };
+constexpr int MAX_EPI_WARPS = 8;
+constexpr int MAX_GEMM_THREADS = 32 * (2 + MAX_EPI_WARPS);
 constexpr int SMEM_LIMIT = 232448;           // 227 KB opt-in dynamic shared memory per CTA
 
 constexpr int RES_BUFS = 4;      // residual epilogue: in-place staging buffers per warp
@@ -29,13 +33,16 @@ constexpr int RES_PREFETCH = 2;  // residual chunks requested ahead of use
 
 template <int BLOCK_N, int EPI, typename OutT, bool DUAL>
 struct GemmSmem {
-  static constexpr int OUT_BUFS = EPI == EPI_RESID ? RES_BUFS : 2;
+  static constexpr int NUM_EPI_WARPS = EpiCfg<EPI>::WARPS;
+  static constexpr int COLS_PER_WARP = BLOCK_N / (NUM_EPI_WARPS / 4);   // columns of the tile one warp handles
+  static constexpr int OUT_BUFS = EPI == EPI_RESID ? RES_BUFS : (NUM_EPI_WARPS == 8 ? 1 : 2);
   static constexpr int B_TILE_BYTES = BLOCK_N * TILE_K_BYTES;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int OUT_STAGE_BYTES = 32 * EPI_COLS * (int)sizeof(OutT);          // per warp per buffer
   static constexpr int OUT2_STAGE_BYTES = DUAL ? 32 * EPI_COLS * 2 : 0;
   static constexpr int STAGING_BYTES = NUM_EPI_WARPS * (OUT_BUFS * OUT_STAGE_BYTES + 2 * OUT2_STAGE_BYTES);
-  static constexpr int BIAS_BYTES = NUM_EPI_WARPS * BLOCK_N * 4;   // per-warp copy of the tile's bias slice
+  static constexpr int BIAS_BYTES = 2 * NUM_EPI_WARPS * COLS_PER_WARP * 4;   // per-warp copies of its slice of the
+                                                                             // bias and folded-LN column sums
   static constexpr int BAR_BYTES = 1024;
   static constexpr int ALIGN_SLACK = 1024;
   static constexpr int RAW_STAGES = (SMEM_LIMIT - STAGING_BYTES - BIAS_BYTES - BAR_BYTES - ALIGN_SLACK) / STAGE_BYTES;
@@ -52,6 +59,11 @@ struct TcArgs {
   int round_tf32;
   // implicit-GEMM convolution (cin_blocks == 0: plain GEMM)
   int cin_blocks, Ho, Wo, tw, th, stride;
+  // folded LayerNorm (consumer side) / row statistics (producer side)
+  const float* ln_stats;
+  int ln_np, ln_d;
+  const float* ln_colsum;
+  float* stats_out;
 };
 
 template <typename OutT>
@@ -83,11 +95,12 @@ __device__ __forceinline__ void stage_row_chunk<bf16>(uint8_t* buf, uint32_t lan
 }
 
 template <typename InT, int BLOCK_N, int EPI, typename OutT, bool DUAL>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(32 * (2 + EpiCfg<EPI>::WARPS), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
                     const __grid_constant__ CUtensorMap tmRes, const TcArgs args) {
   using SM = GemmSmem<BLOCK_N, EPI, OutT, DUAL>;
+  constexpr int NUM_EPI_WARPS = SM::NUM_EPI_WARPS;
   constexpr int STAGES = SM::STAGES;
   constexpr int BLOCK_K = TILE_K_BYTES / (int)sizeof(InT);     // 64 (bf16) or 32 (tf32)
   constexpr int TMEM_COLS = NUM_ACC_STAGES * BLOCK_N;          // 128 / 256 / 512
@@ -198,23 +211,58 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------------------------------------------ epilogue warps
     const uint32_t q = warp & 3;                   // TMEM lane quarter this warp may access
     const uint32_t ew = warp - 2;                  // staging slot
-    constexpr int CH = BLOCK_N / EPI_COLS;
+    const uint32_t half = ew >> 2;                 // which slice of the tile's columns (8-warp epilogues: 0 / 1)
+    constexpr int CH = SM::COLS_PER_WARP / EPI_COLS;   // 32-column chunks per warp per tile
+    const int col_base = half * SM::COLS_PER_WARP;
     uint8_t* st0 = staging + ew * SM::OUT_BUFS * SM::OUT_STAGE_BYTES;
     uint8_t* st1 = staging + NUM_EPI_WARPS * SM::OUT_BUFS * SM::OUT_STAGE_BYTES + ew * 2 * SM::OUT2_STAGE_BYTES;
     uint32_t as = 0, aphase = 0;
-    float* sbias = bias_smem + ew * BLOCK_N;
+    float* sbias = bias_smem + ew * SM::COLS_PER_WARP;
+    float* scsum = bias_smem + (NUM_EPI_WARPS + ew) * SM::COLS_PER_WARP;
     const bool has_bias = args.bias != nullptr;
+    const bool has_ln = args.ln_stats != nullptr;
+    float ln_r = 1.f, ln_t = 0.f;   // per-row rstd and -rstd*mean of the folded LayerNorm
     // stage this tile's bias slice in shared memory (per warp) BEFORE waiting for the accumulator, so the
     // global-load latency hides behind the MMA of the tile
     auto stage_bias = [&](int n_blk) {
-      if (has_bias) {
+      if (has_bias || has_ln) {
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < BLOCK_N / 32; ++i) sbias[i * 32 + lane] = __ldg(args.bias + n_blk * BLOCK_N + i * 32 + lane);
+        for (int i = 0; i < SM::COLS_PER_WARP / 32; ++i) {
+          if (has_bias) sbias[i * 32 + lane] = __ldg(args.bias + n_blk * BLOCK_N + col_base + i * 32 + lane);
+          if (has_ln) scsum[i * 32 + lane] = __ldg(args.ln_colsum + n_blk * BLOCK_N + col_base + i * 32 + lane);
+        }
         __syncwarp();
       }
     };
+    // folded LayerNorm: reduce this row's partial statistics (fixed order) to rstd and -rstd*mean
+    auto load_row_stats = [&](int row) {
+      if (has_ln) {
+        float s1 = 0.f, s2 = 0.f;
+        if (row < args.M) {
+          const float2* sp = reinterpret_cast<const float2*>(args.ln_stats) + (int64_t)row * args.ln_np;
+          for (int i = 0; i < args.ln_np; ++i) { const float2 p = __ldg(sp + i); s1 += p.x; s2 += p.y; }
+        }
+        const float inv_d = 1.f / (float)args.ln_d;
+        const float mean = s1 * inv_d;
+        const float var = fmaxf(s2 * inv_d - mean * mean, 0.f);
+        ln_r = rsqrtf(var + 1e-5f);
+        ln_t = -ln_r * mean;
+      }
+    };
     auto add_bias = [&](float (&v)[EPI_COLS], int c) {
+      if (has_ln) {
+        // v = rstd * acc + (-rstd * mean) * colsum[n]   (then the bias, which already holds beta . W^T)
+        const float4* cp = reinterpret_cast<const float4*>(scsum + c * EPI_COLS);
+#pragma unroll
+        for (int j = 0; j < EPI_COLS / 4; ++j) {
+          const float4 cs = cp[j];
+          v[4 * j] = fmaf(v[4 * j], ln_r, ln_t * cs.x);
+          v[4 * j + 1] = fmaf(v[4 * j + 1], ln_r, ln_t * cs.y);
+          v[4 * j + 2] = fmaf(v[4 * j + 2], ln_r, ln_t * cs.z);
+          v[4 * j + 3] = fmaf(v[4 * j + 3], ln_r, ln_t * cs.w);
+        }
+      }
       if (has_bias) {
         const float4* bp = reinterpret_cast<const float4*>(sbias + c * EPI_COLS);
 #pragma unroll
@@ -249,6 +297,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         stage_bias(n_blk);
         mbar_wait(&acc_full[as], aphase);
         tc_fence_after();
+        float rs1 = 0.f, rs2 = 0.f;   // partial {sum, sumsq} of this thread's row over the tile's columns
 #pragma unroll 1
         for (int c = 0; c < CH; ++c, ++g) {
           const int col0 = n_blk * BLOCK_N + c * EPI_COLS;
@@ -280,6 +329,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             v[4 * j] += x4.x; v[4 * j + 1] += x4.y; v[4 * j + 2] += x4.z; v[4 * j + 3] += x4.w;
             *p = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
+          if (args.stats_out != nullptr) {
+#pragma unroll
+            for (int j = 0; j < EPI_COLS; ++j) { rs1 += v[j]; rs2 = fmaf(v[j], v[j], rs2); }
+          }
           if (DUAL) stage_row_chunk<bf16>(st1 + (g & 1) * SM::OUT2_STAGE_BYTES, lane, v);
           fence_proxy_async_smem();
           __syncwarp();
@@ -289,6 +342,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_store_commit();
           }
         }
+        if (args.stats_out != nullptr && row0 + (int)lane < args.M) {
+          reinterpret_cast<float2*>(args.stats_out)[(int64_t)(row0 + lane) * num_n + n_blk] = make_float2(rs1, rs2);
+        }
         if (++as == NUM_ACC_STAGES) { as = 0; aphase ^= 1; }
       }
     } else {
@@ -297,15 +353,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int m_blk = tile / num_n, n_blk = tile % num_n;
         const int row0 = m_blk * BLOCK_M + q * 32;
         stage_bias(n_blk);
+        load_row_stats(row0 + (int)lane);
         mbar_wait(&acc_full[as], aphase);
         tc_fence_after();
-        const uint32_t acc_addr = tmem_base + ((q * 32u) << 16) + as * BLOCK_N;
+        const uint32_t acc_addr = tmem_base + ((q * 32u) << 16) + as * BLOCK_N + col_base;
         uint32_t rr[2][EPI_COLS];
         tmem_ld_32x32b_x32(acc_addr, rr[0]);
         // one chunk: wait for its TMEM load, start the next chunk's load (overlaps the math), bias / activation,
         // swizzled staging, TMA store
         auto do_chunk = [&](uint32_t (&r)[EPI_COLS], uint32_t (&rnext)[EPI_COLS], int c) {
-          const int col0 = n_blk * BLOCK_N + c * EPI_COLS;
+          const int col0 = n_blk * BLOCK_N + col_base + c * EPI_COLS;
           tmem_ld_wait();
           if (c + 1 < CH) tmem_ld_32x32b_x32(acc_addr + (c + 1) * EPI_COLS, rnext);
           if (c == CH - 1) {
@@ -331,8 +388,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < EPI_COLS; ++j) v[j] = tf32_rn(v[j]);
           }
-          // staging buffer `buf` was last used two steps ago: allow at most one newer bulk group in flight
-          if (lane == 0) tma_store_wait_read<1>();
+          // the staging buffer about to be written was last stored from OUT_BUFS steps ago
+          if (lane == 0) tma_store_wait_read<SM::OUT_BUFS - 1>();
           __syncwarp();
           stage_row_chunk<OutT>(st0 + buf * SM::OUT_STAGE_BYTES, lane, v);
           fence_proxy_async_smem();
@@ -341,12 +398,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_store_2d(&tmOut, st0 + buf * SM::OUT_STAGE_BYTES, col0, row0);
             tma_store_commit();
           }
-          buf ^= 1;
+          if (SM::OUT_BUFS > 1) buf ^= 1;
         };
 #pragma unroll 1
         for (int c2 = 0; c2 < CH; c2 += 2) {
           do_chunk(rr[0], rr[1], c2);
-          do_chunk(rr[1], rr[0], c2 + 1);
+          if (c2 + 1 < CH) do_chunk(rr[1], rr[0], c2 + 1);
         }
         if (++as == NUM_ACC_STAGES) { as = 0; aphase ^= 1; }
       }
@@ -409,14 +466,15 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
   if (!cached_sms) cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev);
   sms = cached_sms > 0 ? cached_sms : 148;
   const int grid = num_tiles < sms ? num_tiles : sms;
-  TcArgs t{a.M, a.N, a.K, a.bias, a.resid, a.ldr, a.round_out_tf32, 0, 0, 0, 0, 0, 1};
+  TcArgs t{a.M, a.N, a.K, a.bias, a.resid, a.ldr, a.round_out_tf32, 0, 0, 0, 0, 0, 1, nullptr, 0, 0, nullptr, nullptr};
   if (a.conv) {
     t.cin_blocks = a.conv->Cin / BLOCK_K;
     t.Ho = a.conv->Ho; t.Wo = a.conv->Wo; t.tw = tw; t.th = th; t.stride = a.conv->stride;
   }
+  t.ln_stats = a.ln_stats; t.ln_np = a.ln_np; t.ln_d = a.ln_d; t.ln_colsum = a.ln_colsum; t.stats_out = a.stats_out;
   g_gemm_flops_issued += 2.0 * a.M * (double)a.N * a.K;
   const int cat = EPI == EPI_RESID ? PC_GEMM_RESID : (EPI == EPI_GELU ? PC_GEMM_GELU : PC_GEMM_STORE);
-  GN_CUDA_CHECK(launch_kernel(cat, kern, dim3(grid), dim3(GEMM_THREADS), SM::TOTAL, stream, tmA, tmB, tmO, tmO2, tmR, t));
+  GN_CUDA_CHECK(launch_kernel(cat, kern, dim3(grid), dim3(32 * (2 + SM::NUM_EPI_WARPS)), SM::TOTAL, stream, tmA, tmB, tmO, tmO2, tmR, t));
   ++g_launch_count;
   return GN_OK;
 }
@@ -522,11 +580,21 @@ int launch_simt(const LinearArgs& a, cudaStream_t s) {
 
 }  // namespace
 
+int resid_block_n(int N, int K, bool dual) {
+  if (N % 256 == 0 && K >= 1024 && !dual) return 256;
+  if (N % 128 == 0) return 128;
+  return 64;
+}
+
 int linear_forward(const LinearArgs& a, cudaStream_t stream) {
   GN_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "linear_forward: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
   GN_REQUIRE(a.A && a.W && a.out, "linear_forward: null operand");
   GN_REQUIRE(a.epi != EPI_RESID || a.resid, "linear_forward: EPI_RESID needs a residual pointer");
   const int esz = a.in_bf16 ? 2 : 4;
+  GN_REQUIRE(!(a.ln_stats || a.stats_out) || (!a.force_simt && a.N % 64 == 0),
+             "folded LayerNorm / row statistics need the tensor path (N %% 64 == 0)");
+  GN_REQUIRE(!a.ln_stats || (a.ln_colsum && a.ln_np > 0 && a.ln_d > 0 && a.epi != EPI_RESID), "bad folded-LayerNorm arguments");
+  GN_REQUIRE(!a.stats_out || a.epi == EPI_RESID, "row statistics are produced by the residual epilogue");
   if (a.conv) {
     const ConvGeom& g = *a.conv;
     const int bk = 128 / esz;

@@ -45,6 +45,15 @@ struct LinearArgs {
   int force_simt;     // 1: CUDA-core fp32 path regardless of shape
   int round_out_tf32; // 1: round the fp32 output to tf32 (it feeds a kind::tf32 GEMM next)
   const ConvGeom* conv; // non-null: implicit-GEMM 3x3 convolution (A = NHWC input, K = 9*Cin, M = Nimg*Ho*Wo)
+  // LayerNorm folded into the epilogue (A holds the RAW bf16 rows, W holds W*diag(gamma)):
+  //   out[m,n] = rstd[m] * (acc[m,n] - mean[m] * colsum[n]) + bias[n]        (bias already contains beta . W^T)
+  // row statistics come as `ln_np` partial {sum, sumsq} pairs per row (written by the previous residual epilogue)
+  const float* ln_stats;  // [M, ln_np, 2] or nullptr
+  int ln_np;
+  int ln_d;               // normalised width (d_model)
+  const float* ln_colsum; // [N]
+  // residual epilogue: also emit per-row partial statistics of the new residual stream: [M, N/BLOCK_N, 2]
+  float* stats_out;
 };
 
 // Enqueue on `stream`.  Returns GN_OK or a negative code (message via last_error()).
@@ -56,6 +65,9 @@ int linear_forward(const LinearArgs& a, cudaStream_t stream);
 int profile_begin();
 int profile_end(double* out);   // see runtime.cu: per-category {ms, launches}
 extern double g_gemm_flops_issued;   // 2*M*N*K summed over tensor-path launches (reset by the caller)
+
+// BLOCK_N the tensor path uses for a residual-epilogue GEMM (= number of stats_out partials per row is N / this)
+int resid_block_n(int N, int K, bool dual);
 
 // number of kernels launched by linear_forward so far (bench's gpu_launches accounting)
 extern unsigned long long g_launch_count;

@@ -12,6 +12,12 @@ int launch_embed(const int32_t* ids, const float* E, const float* mask_embed, co
                  int T, int S, int t0, int Tact, int d, int V, int NV, int mask_id, cudaStream_t st);
 int launch_prep(const float* x, void* out, int out_bf16, const float* gamma, const float* beta, int n_rows, int d,
                 float scale, int S, int Tact, int tsel, cudaStream_t st, int round_tf32 = 0);
+// prep variant that also writes the row statistics {sum, sumsq} (1 partial per row) next to the bf16 cast
+int launch_prep_stats(const float* x, bf16* out, float* stats, int n_rows, int d, cudaStream_t st);
+// fold LayerNorm(gamma, beta) into a linear layer: Wf = bf16(W * diag(gamma)), colsum[n] = sum_k float(Wf[n,k]),
+// bias_f[n] = sum_k beta[k] * W[n,k] + bias[n]
+int launch_fold_ln(const float* W, const float* gamma, const float* beta, const float* bias, bf16* Wf, float* colsum,
+                   float* bias_f, int N, int K, cudaStream_t st);
 int launch_cast_bf16(const float* in, bf16* out, int64_t n, cudaStream_t st);
 int launch_round_tf32(const float* in, float* out, int64_t n, cudaStream_t st);
 int launch_logits_transpose(const float* rows, float* out, int B, int Tl, int S, int C, int Tout, int tslot0,

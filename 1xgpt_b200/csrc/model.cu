@@ -39,6 +39,10 @@ struct LayerW {
   float* fc1_b = nullptr;
   void* fc2_w = nullptr;
   float* fc2_b = nullptr;
+  // folded LayerNorm (bf16, pre-LN): fp32 masters + W*diag(gamma) / column sums / folded bias
+  float *qkv_s_raw = nullptr, *fc1_raw = nullptr;
+  bf16 *qkv_s_f = nullptr, *fc1_f = nullptr;
+  float *qkv_s_cs = nullptr, *qkv_s_bf = nullptr, *fc1_cs = nullptr, *fc1_bf = nullptr;
 };
 
 }  // namespace
@@ -65,6 +69,9 @@ struct gn_model {
   void* a = nullptr;      // [n, d] act
   void* big = nullptr;    // [n, max(3d, hid)] act (qkv / mlp hidden)
   void* o = nullptr;      // [n, d] act
+  float* stats = nullptr; // [n, d/64, 2] row-statistics partials for the folded LayerNorm
+  int fold = 0;           // folded-LayerNorm path active (bf16, qk_norm = 0, cfg.fold_ln)
+  bool fold_dirty = true;
   int64_t rows_cap = 0;
   float* rows = nullptr;  // [rows_cap, C] fp32 logits rows
 
@@ -111,12 +118,13 @@ int ensure_workspace(gn_model* m, int64_t n) {
   if (n <= m->ws_tokens) return GN_OK;
   const int d = m->cfg.d_model;
   const int64_t wide = std::max<int64_t>(3 * d, m->hid);
-  dev_free(m, m->x); dev_free(m, m->a); dev_free(m, m->big); dev_free(m, m->o);
+  dev_free(m, m->x); dev_free(m, m->a); dev_free(m, m->big); dev_free(m, m->o); dev_free(m, m->stats);
   m->ws_tokens = 0;
   GN_PROPAGATE(dev_alloc(m, (void**)&m->x, (size_t)n * d * 4));
   GN_PROPAGATE(dev_alloc(m, &m->a, (size_t)n * d * m->esz()));
   GN_PROPAGATE(dev_alloc(m, &m->big, (size_t)n * wide * m->esz()));
   GN_PROPAGATE(dev_alloc(m, &m->o, (size_t)n * d * m->esz()));
+  GN_PROPAGATE(dev_alloc(m, (void**)&m->stats, (size_t)n * (d / 64 + 1) * 2 * sizeof(float)));
   m->ws_tokens = n;
   return GN_OK;
 }
@@ -162,9 +170,21 @@ int chunk_clips_for(const gn_model* m, int Tact) {
   return c < 1 ? 1 : c;
 }
 
+struct LnFold {
+  const float* stats = nullptr;   // consumer: row-statistics partials
+  int np = 0;
+  const float* colsum = nullptr;
+  float* stats_out = nullptr;     // producer (residual epilogue)
+};
+
 int linear(gn_model* m, const void* A, int64_t lda, const void* W, int K, const float* bias, const float* resid,
-           void* out, int64_t ldo, void* out2, int M, int N, int epi, int out_bf16, cudaStream_t st) {
+           void* out, int64_t ldo, void* out2, int M, int N, int epi, int out_bf16, cudaStream_t st,
+           const LnFold* lf = nullptr) {
   LinearArgs la{};
+  if (lf) {
+    la.ln_stats = lf->stats; la.ln_np = lf->np; la.ln_d = m->cfg.d_model; la.ln_colsum = lf->colsum;
+    la.stats_out = lf->stats_out;
+  }
   la.A = A; la.lda = lda; la.W = W; la.ldw = K; la.bias = bias; la.resid = resid; la.ldr = N;
   la.out = out; la.ldo = ldo; la.out2 = out2; la.ldo2 = N;
   la.M = M; la.N = N; la.K = K; la.epi = epi; la.in_bf16 = m->act_bf16; la.out_bf16 = out_bf16;
@@ -183,6 +203,67 @@ int run_layers(gn_model* m, int b0, int nb, int t0, int Tact, bool use_cache, cu
   const int bf = m->act_bf16;
   const float scale = c.use_mup ? 8.0f / hd : 1.0f / sqrtf((float)hd);
   const int tf = m->tf32;
+  if (m->fold) {
+    // ---- bf16, pre-LN, LayerNorm folded into the QKV / fc1 epilogues: no stand-alone LayerNorm pass.
+    // m->a always holds bf16(x) (emitted by the residual epilogues), m->stats the row statistics of x.
+    if (m->fold_dirty) {
+      for (int l = 0; l < c.num_layers; ++l) {
+        LayerW& w = m->layers[l];
+        const size_t nq = (size_t)3 * d * d, nf = (size_t)m->hid * d;
+        if (!w.qkv_s_f) {
+          GN_PROPAGATE(dev_alloc(m, (void**)&w.qkv_s_f, nq * 2));
+          GN_PROPAGATE(dev_alloc(m, (void**)&w.qkv_s_cs, (size_t)3 * d * 4));
+          GN_PROPAGATE(dev_alloc(m, (void**)&w.qkv_s_bf, (size_t)3 * d * 4));
+          GN_PROPAGATE(dev_alloc(m, (void**)&w.fc1_f, nf * 2));
+          GN_PROPAGATE(dev_alloc(m, (void**)&w.fc1_cs, (size_t)m->hid * 4));
+          GN_PROPAGATE(dev_alloc(m, (void**)&w.fc1_bf, (size_t)m->hid * 4));
+        }
+        GN_PROPAGATE(launch_fold_ln(w.qkv_s_raw, w.ln1_g, w.ln1_b, w.attn[0].qkv_b, w.qkv_s_f, w.qkv_s_cs, w.qkv_s_bf,
+                                    3 * d, d, st));
+        GN_PROPAGATE(launch_fold_ln(w.fc1_raw, w.ln2_g, w.ln2_b, w.fc1_b, w.fc1_f, w.fc1_cs, w.fc1_bf, m->hid, d, st));
+      }
+      m->fold_dirty = false;
+    }
+    GN_PROPAGATE(launch_prep_stats(m->x, (bf16*)m->a, m->stats, n, d, st));
+    int np = 1;
+    const int np_d = d / resid_block_n(d, d, true);
+    for (int l = 0; l < c.num_layers; ++l) {
+      const LayerW& w = m->layers[l];
+      LnFold lf{};
+      lf.stats = m->stats; lf.np = np; lf.colsum = w.qkv_s_cs;
+      GN_PROPAGATE(linear(m, m->a, d, w.qkv_s_f, d, w.qkv_s_bf, nullptr, m->big, 3 * d, nullptr, n, 3 * d, EPI_STORE, 1,
+                          st, &lf));
+      AttnArgs aa{};
+      aa.qkv = m->big; aa.out = m->o; aa.act_bf16 = 1; aa.n_heads = H; aa.head_dim = hd; aa.scale = scale;
+      GN_PROPAGATE(launch_spatial_attention(aa, nb * Tact, S, c.generic_attention, st));
+      m->flops_executed += 4.0 * S * (double)d * n;
+      GN_PROPAGATE(linear(m, m->o, d, w.attn[0].proj_w, d, w.attn[0].proj_b, m->x, m->x, d, m->a, n, d, EPI_RESID, 0, st));
+      GN_PROPAGATE(linear(m, m->a, d, w.attn[1].qkv_w, d, w.attn[1].qkv_b, nullptr, m->big, 3 * d, nullptr, n, 3 * d,
+                          EPI_STORE, 1, st));
+      void *kc = nullptr, *vc = nullptr;
+      if (use_cache) {
+        const size_t layer_stride = (size_t)m->cache_B * T * S * d * m->esz();
+        const size_t clip_off = (size_t)b0 * T * S * d * m->esz();
+        kc = (char*)m->kcache + l * layer_stride + clip_off;
+        vc = (char*)m->vcache + l * layer_stride + clip_off;
+      }
+      GN_PROPAGATE(launch_temporal_attention(aa, nb, S, T, t0, Tact, kc, vc, c.generic_attention, st));
+      m->flops_executed += 4.0 * (t0 + Tact) * (double)d * n;
+      LnFold ps{};
+      ps.stats_out = m->stats;
+      GN_PROPAGATE(linear(m, m->o, d, w.attn[1].proj_w, d, w.attn[1].proj_b, m->x, m->x, d, m->a, n, d, EPI_RESID, 0, st,
+                          &ps));
+      LnFold lf2{};
+      lf2.stats = m->stats; lf2.np = np_d; lf2.colsum = w.fc1_cs;
+      GN_PROPAGATE(linear(m, m->a, d, w.fc1_f, d, w.fc1_bf, nullptr, m->big, m->hid, nullptr, n, m->hid, EPI_GELU, 1, st,
+                          &lf2));
+      const bool last = l + 1 == c.num_layers;
+      GN_PROPAGATE(linear(m, m->big, m->hid, w.fc2_w, m->hid, w.fc2_b, m->x, m->x, d, last ? nullptr : m->a, n, d,
+                          EPI_RESID, 0, st, last ? nullptr : &ps));
+      np = np_d;
+    }
+    return GN_OK;
+  }
   const bool cp = bf || tf;  // GEMM A operands need a converted copy of the fp32 stream (bf16 cast / tf32 rounding)
   bool a_is_x = false;       // does m->a currently hold convert(x)?
   for (int l = 0; l < c.num_layers; ++l) {
@@ -413,6 +494,7 @@ int gn_model_create(gn_model** out, const gn_config* cfg, int device) {
   m->act_bf16 = cfg->precision == GN_PREC_BF16;
   m->force_simt = cfg->precision == GN_PREC_FP32;
   m->tf32 = cfg->precision == GN_PREC_TF32;
+  m->fold = (m->act_bf16 && !cfg->qk_norm && cfg->fold_ln && cfg->d_model % 64 == 0) ? 1 : 0;
   m->hid = (int)(cfg->d_model * cfg->mlp_ratio);
   m->C = cfg->num_factored_vocabs * cfg->factored_vocab_size;
   m->layers.resize(cfg->num_layers);
@@ -434,6 +516,7 @@ int gn_model_set_weight(gn_model* m, const char* key, const float* src, const in
   cudaStream_t st = (cudaStream_t)stream;
   const gn_config& c = m->cfg;
   const int d = c.d_model, hd = d / c.num_heads;
+  m->fold_dirty = true;
   int64_t numel = 1;
   for (int i = 0; i < ndim; ++i) numel *= shape[i];
   std::string k(key);
@@ -486,7 +569,10 @@ int gn_model_set_weight(gn_model* m, const char* key, const float* src, const in
       if (r.rfind(p, 0) != 0) continue;
       const std::string t = r.substr(p.size());
       AttnW& a = w.attn[which];
-      if (t == "qkv.weight") return put_mat(&a.qkv_w, (int64_t)3 * d * d);
+      if (t == "qkv.weight") {
+        if (which == 0 && m->fold) { GN_PROPAGATE(put_f32(&w.qkv_s_raw, (int64_t)3 * d * d)); m->have.erase(k); }
+        return put_mat(&a.qkv_w, (int64_t)3 * d * d);
+      }
       if (t == "qkv.bias") return put_f32(&a.qkv_b, 3 * d);
       if (t == "proj.weight") return put_mat(&a.proj_w, (int64_t)d * d);
       if (t == "proj.bias") return put_f32(&a.proj_b, d);
@@ -497,7 +583,10 @@ int gn_model_set_weight(gn_model* m, const char* key, const float* src, const in
     if (r == "norm1.bias") return put_f32(&w.ln1_b, d);
     if (r == "norm2.weight") return put_f32(&w.ln2_g, d);
     if (r == "norm2.bias") return put_f32(&w.ln2_b, d);
-    if (r == "mlp.fc1.weight") return put_mat(&w.fc1_w, (int64_t)m->hid * d);
+    if (r == "mlp.fc1.weight") {
+      if (m->fold) { GN_PROPAGATE(put_f32(&w.fc1_raw, (int64_t)m->hid * d)); m->have.erase(k); }
+      return put_mat(&w.fc1_w, (int64_t)m->hid * d);
+    }
     if (r == "mlp.fc1.bias") return put_f32(&w.fc1_b, m->hid);
     if (r == "mlp.fc2.weight") return put_mat(&w.fc2_w, (int64_t)d * m->hid);
     if (r == "mlp.fc2.bias") return put_f32(&w.fc2_b, d);

@@ -169,10 +169,13 @@ class STMaskGIT(nn.Module):
                         bit-identical tokens, ~8-10x fewer FLOPs (reference recomputes the full window)
       chunk_tokens      tokens per L2-resident work chunk (0 = default 16384)
       generic_attention force the CUDA-core attention kernels
+      fold_ln           bf16 + pre-LN configs: apply norm1 / norm2 inside the QKV / fc1 GEMM epilogues instead of a
+                        separate pass (same accuracy; measured neutral on B200 because the residual GEMMs then lose
+                        their 256-wide tile, so it is off by default)
     """
 
     def __init__(self, config: GenieConfig, precision: str = "bf16", kv_cache: bool = False, chunk_tokens: int = 0,
-                 generic_attention: bool = False):
+                 generic_attention: bool = False, fold_ln: bool = False):
         super().__init__()
         self.h = self.w = math.isqrt(config.S)
         assert self.h ** 2 == config.S, "Expected S to be square"
@@ -194,6 +197,7 @@ class STMaskGIT(nn.Module):
         self.kv_cache = bool(kv_cache)
         self.chunk_tokens = int(chunk_tokens)
         self.generic_attention = bool(generic_attention)
+        self.fold_ln = bool(fold_ln)
         self.__dict__["_native"] = None
         self.__dict__["_native_key"] = None
         self.__dict__["_weights_dirty"] = True
@@ -233,7 +237,7 @@ class STMaskGIT(nn.Module):
             proj_bias=int(c.proj_bias), qk_norm=int(c.qk_norm), mlp_bias=int(c.mlp_bias),
             mlp_ratio=float(c.mlp_ratio), precision=_lib.PRECISIONS[self.precision],
             chunk_tokens=self.chunk_tokens, kv_cache=int(self.kv_cache),
-            generic_attention=int(self.generic_attention))
+            generic_attention=int(self.generic_attention), fold_ln=int(self.fold_ln))
 
     def _handle(self) -> _NativeHandle:
         dev = self.device
@@ -242,7 +246,7 @@ class STMaskGIT(nn.Module):
                 "the GENIE B200 path runs on a CUDA device only (model is on "
                 f"{dev}); move it with .to('cuda').  There is no CPU fallback.")
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
-        key = (idx, self.precision, self.kv_cache, self.chunk_tokens, self.generic_attention)
+        key = (idx, self.precision, self.kv_cache, self.chunk_tokens, self.generic_attention, self.fold_ln)
         d = self.__dict__
         if d["_native"] is None or d["_native_key"] != key:
             d["_native"] = _NativeHandle(self._gn_config(), idx)

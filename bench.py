@@ -199,6 +199,7 @@ def main():
                          "full 16-frame window every MaskGIT step like the reference")
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
     ap.add_argument("--chunk-tokens", type=int, default=32768)
+    ap.add_argument("--fold-ln", action="store_true", help="LayerNorm folded into the QKV/fc1 GEMM epilogues")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary (other mode) measurement")
     args = ap.parse_args()
@@ -225,7 +226,7 @@ def main():
 
     def make_model(mode):
         m = pkg.STMaskGIT(pkg.GenieConfig(**MODEL_KW), precision="bf16", kv_cache=(mode == "cached"),
-                          chunk_tokens=args.chunk_tokens)
+                          chunk_tokens=args.chunk_tokens, fold_ln=args.fold_ln)
         m.load_state_dict(sd)
         return m.to(dev)
 

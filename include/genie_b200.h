@@ -57,6 +57,9 @@ typedef struct gn_config {
                             results, fewer FLOPs); 0: recompute the full T-frame window every step like the
                             reference (st_mask_git.py:163,169) */
   int32_t generic_attention; /* 1: force the CUDA-core attention kernels (debug / cross-check) */
+  int32_t fold_ln;       /* bf16 mode, pre-LN configs (qk_norm = 0): 1 = apply norm1 / norm2 inside the epilogue of the
+                            QKV / fc1 GEMM (W*diag(gamma) folded into the weights, row statistics produced by the
+                            previous residual epilogue) instead of a separate LayerNorm pass; 0 = separate pass */
 } gn_config;
 
 int gn_version(void);

@@ -186,6 +186,26 @@ def test_reference_attention_cases():
         assert torch.allclose(y2.cpu(), torch.from_numpy(z["y_full"]), atol=2e-6)
 
 
+@pytest.mark.parametrize("name", ["tiny_preln", "genie35m"])
+def test_folded_layernorm_option(name):
+    """fold_ln=True (LayerNorm inside the QKV / fc1 GEMM epilogues) matches the separate-pass path."""
+    if name.startswith("tiny"):
+        z = load_golden(name)
+        kw, sd = golden_cfg(z), golden_sd(z)
+        ids = torch.from_numpy(z["prompt"])
+        ref = torch.from_numpy(z["logits"])
+    else:
+        z, kw, cfg, sd = _prod_setup(name)
+        ids = torch.from_numpy(z["ids"]).long()
+        ref = None
+    a = build_b200_model(kw, sd, precision="bf16", fold_ln=True).compute_logits(ids.cuda())
+    b = build_b200_model(kw, sd, precision="bf16", fold_ln=False).compute_logits(ids.cuda())
+    print(f"{name}: fold vs separate LN rel {rel_fro(a, b):.3e}")
+    assert rel_fro(a, b) < 1e-2
+    if ref is not None:
+        assert rel_fro(a, ref) < TOL["bf16"]
+
+
 def test_decoder_forward_seam():
     z = load_golden("tiny_qknorm")
     kw, sd = golden_cfg(z), golden_sd(z)
