@@ -257,3 +257,21 @@ def test_wide_model_shapes_d1024_h16(qk_norm, use_mup):
         s, _ = m.maskgit_generate(p, 12, maskgit_steps=8, temperature=0.0, noise=noise)
         outs.append(s.cpu())
     assert torch.equal(outs[0], outs[1])
+
+
+def test_production_teacher_forced_ce_parity_35m():
+    """BASELINE 'teacher-forced CE parity' on the in-tree 35M config (evaluate.py:82-122,173-179 semantics):
+    CE / accuracy of the fused GPU evaluation (bf16, K/V cache) against the CPU oracle (fp32) on one clip."""
+    z, kw, cfg, sd = _prod_setup("genie35m")
+    ids = torch.from_numpy(z["ids"]).long()[:1]
+    noise = torch.stack([O.tie_free_noise(2, 1, cfg.S, seed=700 + t) for t in range(cfg.T - 1)])
+    loss, acc, samples = O.teacher_forced_metrics(sd, cfg, ids.reshape(1, -1), 2, noise)
+    m = build_b200_model(kw, sd, precision="bf16", kv_cache=True)
+    a, s = m.teacher_forced_eval(ids.reshape(1, -1).cuda(), maskgit_steps=2, noise=noise, return_samples=True)
+    a = a.cpu()
+    ce = a[0].item() / a[1].item()
+    agree = float((s.cpu() == samples).float().mean())
+    print(f"35M teacher-forced CE: gpu(bf16) {ce:.5f} vs oracle(fp32) {loss:.5f}; token agreement {agree:.4f}; "
+          f"acc {a[3].item() / a[1].item():.5f} vs {acc:.5f}")
+    assert abs(ce - loss) < 2e-3 * loss          # CE is an average over 3840 tokens: bf16 noise averages out
+    assert agree > 0.9
