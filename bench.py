@@ -314,6 +314,13 @@ def main():
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     dense_flops_step = model.flops_per_clip_forward() * B * n_new * MASKGIT_STEPS  # reference-equivalent FLOPs / step / GPU
 
+    # DRAM bytes per GEMM launch from the committed ncu --set full capture of the same kernel in situ (profiles/)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_gemm_insitu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("avg_dram_bytes_per_gemm_launch")
+
     secondary = None
     if rank == 0 and world == 1 and not args.no_secondary:
         other = "dense" if args.mode == "cached" else "cached"
@@ -350,7 +357,10 @@ def main():
                                         "126 MB L2; no L2 flush needed",
                        "parallelism": f"dp{world} (clips sharded, no collective)"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                         "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic,
+                         "traffic_note": "avg dram__bytes_read+write per tcgen05 GEMM launch, ncu --set full in situ at "
+                                         "M=32256 (profiles/r01_gemm_insitu_traffic.json); algorithmic bytes per "
+                                         "launch (A + residual + outputs) avg 171 MB at that M",
                          "kernel": "gemm_tcgen05_kernel (all linear layers)", "launches_timed": int(gemm_launches),
                          "kernel_ms_per_step": gemm_ms / args.steps, "kernel_share_of_step": gemm_ms / ms_prof,
                          "profiled_ms_per_step": ms_prof / args.steps, "kernel_ms_by_category": by_cat,
