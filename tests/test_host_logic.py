@@ -95,3 +95,38 @@ def test_generate_writer_reference_format(tmp_path):
     import numpy as np
     raw = np.fromfile(tmp_path / "video.bin", dtype=np.uint32).reshape(24, 4, 4)
     assert (raw[8:16] == g[8:].numpy()).all() and (raw[16:] == ex[8:].numpy()).all()
+
+
+def _write_dataset(tmp_path, n=80, s=4, seg_break=40):
+    import numpy as np
+    rng = np.random.default_rng(0)
+    vid = rng.integers(0, 262144, size=(n, s, s), dtype=np.uint32)
+    vid.tofile(tmp_path / "video.bin")
+    seg = (np.arange(n) >= seg_break).astype(np.int32)
+    seg.tofile(tmp_path / "segment_ids.bin")
+    json.dump({"num_images": n, "s": s, "vocab_size": 262144, "hz": 30, "token_dtype": "uint32"},
+              open(tmp_path / "metadata.json", "w"))
+    return vid, seg
+
+
+def test_raw_token_dataset_windows(tmp_path):
+    data = importlib.import_module("1xgpt_b200.data")
+    vid, seg = _write_dataset(tmp_path)
+    ds = data.RawTokenDataset(tmp_path, window_size=4, stride=5)          # video_len = 15
+    # brute-force expectation (reference semantics, data.py:62-70): window valid iff first and last frame share a segment
+    exp = [st for st in range(80 - 15) if seg[st] == seg[st + 15]]
+    assert ds.valid_start_inds == exp
+    item = ds[3]
+    st = exp[3]
+    assert item["input_ids"].dtype == torch.int64 and item["input_ids"].shape == (4 * 16,)
+    assert (item["input_ids"].reshape(4, 4, 4).numpy() == vid[st:st + 16:5]).all()
+    assert torch.equal(item["labels"], item["input_ids"]) and int(item["attention_mask"].sum()) == 64
+    # de-overlapped variant: no two kept windows share a frame
+    ds2 = data.RawTokenDataset(tmp_path, window_size=4, stride=5, filter_overlaps=True)
+    frames = [set(range(st, st + 16, 5)) for st in ds2.valid_start_inds]
+    assert all(a.isdisjoint(b) for i, a in enumerate(frames) for b in frames[i + 1:])
+    assert len(ds2) > 0 and ds2.valid_start_inds[0] == exp[0]
+    assert ds2.clips().shape == (len(ds2), 64)
+    with pytest.raises(NotImplementedError):
+        os.remove(tmp_path / "segment_ids.bin")
+        data.RawTokenDataset(tmp_path, window_size=4)
