@@ -24,7 +24,7 @@ class gn_config(C.Structure):
         ("factored_vocab_size", C.c_int32), ("use_mup", C.c_int32), ("qkv_bias", C.c_int32),
         ("proj_bias", C.c_int32), ("qk_norm", C.c_int32), ("mlp_bias", C.c_int32), ("mlp_ratio", C.c_float),
         ("precision", C.c_int32), ("chunk_tokens", C.c_int32), ("kv_cache", C.c_int32),
-        ("generic_attention", C.c_int32), ("fold_ln", C.c_int32),
+        ("generic_attention", C.c_int32), ("fold_ln", C.c_int32), ("cuda_graphs", C.c_int32),
     ]
 
 

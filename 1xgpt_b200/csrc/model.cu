@@ -12,16 +12,6 @@
 
 using namespace gn;
 
-namespace gn {
-int generic_temporal_attention(const AttnArgs& a, int B, int S, int T, int t0, int Tq, void* kcache, void* vcache,
-                               cudaStream_t st);
-int fast_spatial_attention(const AttnArgs& a, int n_frames, int S, cudaStream_t st);
-bool fast_spatial_supported(const AttnArgs& a, int S);
-int fast_temporal_attention(const AttnArgs& a, int B, int S, int T, int t0, int Tq, void* kcache, void* vcache,
-                            cudaStream_t st);
-bool fast_temporal_supported(const AttnArgs& a, int T);
-}  // namespace gn
-
 namespace {
 
 struct AttnW {
@@ -97,6 +87,10 @@ struct gn_model {
 
   double flops_executed = 0.0;
 
+  // CUDA graphs of run_layers, keyed by (b0, nb, t0, Tact, use_cache); invalidated when a buffer is reallocated
+  struct GraphEntry { cudaGraphExec_t exec; double flops; unsigned long long launches; };
+  std::map<std::vector<int>, GraphEntry> graphs;
+
   size_t esz() const { return act_bf16 ? 2 : 4; }
 };
 
@@ -114,8 +108,14 @@ void dev_free(gn_model* m, void* p) {
   cudaFree(p);
 }
 
+void drop_graphs(gn_model* m) {
+  for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second.exec);
+  m->graphs.clear();
+}
+
 int ensure_workspace(gn_model* m, int64_t n) {
   if (n <= m->ws_tokens) return GN_OK;
+  drop_graphs(m);
   const int d = m->cfg.d_model;
   const int64_t wide = std::max<int64_t>(3 * d, m->hid);
   dev_free(m, m->x); dev_free(m, m->a); dev_free(m, m->big); dev_free(m, m->o); dev_free(m, m->stats);
@@ -138,6 +138,7 @@ int ensure_rows(gn_model* m, int64_t r) {
 }
 int ensure_cache(gn_model* m, int B) {
   if (B <= m->cache_B) return GN_OK;
+  drop_graphs(m);
   dev_free(m, m->kcache); dev_free(m, m->vcache);
   m->cache_B = 0;
   const size_t bytes = (size_t)m->cfg.num_layers * B * m->cfg.T * m->cfg.S * m->cfg.d_model * m->esz();
@@ -325,13 +326,57 @@ int run_layers(gn_model* m, int b0, int nb, int t0, int Tact, bool use_cache, cu
   return GN_OK;
 }
 
+// run_layers through a CUDA graph: the ~10 launches x L layers of one chunk are captured the first time a
+// (b0, nb, t0, Tact, cache) shape is seen on a capturable stream and replayed afterwards (all pointers they use are
+// model-owned and stable; reallocation drops the graphs).
+int run_layers_graphed(gn_model* m, int b0, int nb, int t0, int Tact, bool use_cache, cudaStream_t st) {
+  if (!m->cfg.cuda_graphs || st == nullptr || st == cudaStreamLegacy || g_prof_on || (m->fold && m->fold_dirty))
+    return run_layers(m, b0, nb, t0, Tact, use_cache, st);
+  const std::vector<int> key = {b0, nb, t0, Tact, use_cache ? 1 : 0};
+  auto it = m->graphs.find(key);
+  if (it == m->graphs.end()) {
+    const double f0 = m->flops_executed;
+    const unsigned long long l0 = g_launch_count;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+      cudaGetLastError();
+      return run_layers(m, b0, nb, t0, Tact, use_cache, st);
+    }
+    const int rc = run_layers(m, b0, nb, t0, Tact, use_cache, st);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc != GN_OK || ce != cudaSuccess || graph == nullptr) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      if (rc != GN_OK) return rc;
+      m->flops_executed = f0;
+      return run_layers(m, b0, nb, t0, Tact, use_cache, st);   // capture not possible here: run eagerly
+    }
+    gn_model::GraphEntry e{};
+    e.flops = m->flops_executed - f0;
+    e.launches = g_launch_count - l0;
+    const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    m->flops_executed = f0;
+    g_launch_count = l0;
+    if (ie != cudaSuccess) {
+      cudaGetLastError();
+      return run_layers(m, b0, nb, t0, Tact, use_cache, st);
+    }
+    it = m->graphs.emplace(key, e).first;
+  }
+  GN_CUDA_CHECK(cudaGraphLaunch(it->second.exec, st));
+  m->flops_executed += it->second.flops;
+  g_launch_count += it->second.launches;
+  return GN_OK;
+}
+
 // embed (+pos) clips [b0, b0+nb), frames [t0, t0+Tact) of ids [B,T,S] into m->x, then the L blocks.
 int forward_chunk(gn_model* m, const int32_t* ids, int b0, int nb, int t0, int Tact, bool use_cache, cudaStream_t st) {
   const gn_config& c = m->cfg;
   GN_PROPAGATE(ensure_workspace(m, (int64_t)nb * Tact * c.S));
   GN_PROPAGATE(launch_embed(ids + (int64_t)b0 * c.T * c.S, m->E, m->mask_embed, m->pos, m->x, nb, c.T, c.S, t0, Tact,
                             c.d_model, c.factored_vocab_size, c.num_factored_vocabs, c.image_vocab_size, st));
-  return run_layers(m, b0, nb, t0, Tact, use_cache, st);
+  return run_layers_graphed(m, b0, nb, t0, Tact, use_cache, st);
 }
 
 // readout of rows (optionally only local frame `tsel`) of m->x into out_rows [R, C] fp32
@@ -505,6 +550,7 @@ int gn_model_create(gn_model** out, const gn_config* cfg, int device) {
 void gn_model_destroy(gn_model* m) {
   if (!m) return;
   DeviceGuard g(m->device);
+  drop_graphs(m);
   for (void* p : m->owned)
     if (p) cudaFree(p);
   delete m;

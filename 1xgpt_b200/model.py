@@ -172,10 +172,12 @@ class STMaskGIT(nn.Module):
       fold_ln           bf16 + pre-LN configs: apply norm1 / norm2 inside the QKV / fc1 GEMM epilogues instead of a
                         separate pass (same accuracy; measured neutral on B200 because the residual GEMMs then lose
                         their 256-wide tile, so it is off by default)
+      cuda_graphs       replay the per-chunk layer stack from a captured CUDA graph when running on a non-default
+                        stream (default on)
     """
 
     def __init__(self, config: GenieConfig, precision: str = "bf16", kv_cache: bool = False, chunk_tokens: int = 0,
-                 generic_attention: bool = False, fold_ln: bool = False):
+                 generic_attention: bool = False, fold_ln: bool = False, cuda_graphs: bool = True):
         super().__init__()
         self.h = self.w = math.isqrt(config.S)
         assert self.h ** 2 == config.S, "Expected S to be square"
@@ -198,6 +200,7 @@ class STMaskGIT(nn.Module):
         self.chunk_tokens = int(chunk_tokens)
         self.generic_attention = bool(generic_attention)
         self.fold_ln = bool(fold_ln)
+        self.cuda_graphs = bool(cuda_graphs)
         self.__dict__["_native"] = None
         self.__dict__["_native_key"] = None
         self.__dict__["_weights_dirty"] = True
@@ -237,7 +240,8 @@ class STMaskGIT(nn.Module):
             proj_bias=int(c.proj_bias), qk_norm=int(c.qk_norm), mlp_bias=int(c.mlp_bias),
             mlp_ratio=float(c.mlp_ratio), precision=_lib.PRECISIONS[self.precision],
             chunk_tokens=self.chunk_tokens, kv_cache=int(self.kv_cache),
-            generic_attention=int(self.generic_attention), fold_ln=int(self.fold_ln))
+            generic_attention=int(self.generic_attention), fold_ln=int(self.fold_ln),
+            cuda_graphs=int(self.cuda_graphs))
 
     def _handle(self) -> _NativeHandle:
         dev = self.device
@@ -246,7 +250,7 @@ class STMaskGIT(nn.Module):
                 "the GENIE B200 path runs on a CUDA device only (model is on "
                 f"{dev}); move it with .to('cuda').  There is no CPU fallback.")
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
-        key = (idx, self.precision, self.kv_cache, self.chunk_tokens, self.generic_attention, self.fold_ln)
+        key = (idx, self.precision, self.kv_cache, self.chunk_tokens, self.generic_attention, self.fold_ln, self.cuda_graphs)
         d = self.__dict__
         if d["_native"] is None or d["_native_key"] != key:
             d["_native"] = _NativeHandle(self._gn_config(), idx)

@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
     ap.add_argument("--chunk-tokens", type=int, default=32768)
     ap.add_argument("--fold-ln", action="store_true", help="LayerNorm folded into the QKV/fc1 GEMM epilogues")
+    ap.add_argument("--no-graphs", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary (other mode) measurement")
     args = ap.parse_args()
@@ -217,6 +218,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # a non-default stream, so the library can capture / replay its per-chunk CUDA graphs
+    torch.cuda.set_stream(torch.cuda.Stream(dev))
     pkg = importlib.import_module("1xgpt_b200")
     lib = pkg._lib.load()
 
@@ -226,7 +229,7 @@ def main():
 
     def make_model(mode):
         m = pkg.STMaskGIT(pkg.GenieConfig(**MODEL_KW), precision="bf16", kv_cache=(mode == "cached"),
-                          chunk_tokens=args.chunk_tokens, fold_ln=args.fold_ln)
+                          chunk_tokens=args.chunk_tokens, fold_ln=args.fold_ln, cuda_graphs=not args.no_graphs)
         m.load_state_dict(sd)
         return m.to(dev)
 

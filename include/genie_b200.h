@@ -60,6 +60,9 @@ typedef struct gn_config {
   int32_t fold_ln;       /* bf16 mode, pre-LN configs (qk_norm = 0): 1 = apply norm1 / norm2 inside the epilogue of the
                             QKV / fc1 GEMM (W*diag(gamma) folded into the weights, row statistics produced by the
                             previous residual epilogue) instead of a separate LayerNorm pass; 0 = separate pass */
+  int32_t cuda_graphs;   /* 1: the per-chunk layer stack (~330 kernel launches) is captured once per shape into a CUDA
+                            graph and replayed (only when the caller's stream is not the legacy default stream);
+                            removes the host launch bound at small batch */
 } gn_config;
 
 int gn_version(void);

@@ -275,3 +275,30 @@ def test_production_teacher_forced_ce_parity_35m():
           f"acc {a[3].item() / a[1].item():.5f} vs {acc:.5f}")
     assert abs(ce - loss) < 2e-3 * loss          # CE is an average over 3840 tokens: bf16 noise averages out
     assert agree > 0.9
+
+
+def test_cuda_graph_replay_is_bit_identical():
+    """On a non-default stream the per-chunk layer stack is captured into a CUDA graph at first use and replayed:
+    tokens and logits must equal the eager launches bit for bit, on capture and on every replay."""
+    z, kw, cfg, sd = _prod_setup("genie35m")
+    ids = torch.from_numpy(z["ids"]).long()
+    B = ids.shape[0]
+    prompt0 = ids.clone()
+    prompt0[:, 8:] = cfg.mask_token_id
+    noise = torch.from_numpy(z["noise"])
+    side = torch.cuda.Stream()
+    outs = {}
+    for graphs in (False, True):
+        m = build_b200_model(kw, sd, precision="bf16", kv_cache=True, cuda_graphs=graphs)
+        runs = []
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                p = prompt0.clone().cuda()
+                s, fl = m.maskgit_generate(p, 8, maskgit_steps=2, temperature=0.0, noise=noise)
+                side.synchronize()
+                runs.append((s.cpu(), fl.cpu().clone()))
+        for r in runs[1:]:
+            assert torch.equal(r[0], runs[0][0]) and torch.equal(r[1], runs[0][1])
+        outs[graphs] = runs[0]
+    assert torch.equal(outs[False][0], outs[True][0])
+    assert torch.equal(outs[False][1], outs[True][1])
