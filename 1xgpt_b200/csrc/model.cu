@@ -166,7 +166,7 @@ int ensure_decode(gn_model* m, int B) {
 }
 
 int chunk_clips_for(const gn_model* m, int Tact) {
-  const int ct = m->cfg.chunk_tokens > 0 ? m->cfg.chunk_tokens : 16384;
+  const int ct = m->cfg.chunk_tokens > 0 ? m->cfg.chunk_tokens : 32768;
   int c = ct / (Tact * m->cfg.S);
   return c < 1 ? 1 : c;
 }

@@ -167,7 +167,7 @@ class STMaskGIT(nn.Module):
       precision         "bf16" (tcgen05 kind::f16, default) | "tf32" (parity mode) | "fp32" (CUDA-core, exact)
       kv_cache          temporal K/V cache + causal frame trimming for maskgit_generate / generate / evaluate:
                         bit-identical tokens, ~8-10x fewer FLOPs (reference recomputes the full window)
-      chunk_tokens      tokens per L2-resident work chunk (0 = default 16384)
+      chunk_tokens      tokens per L2-resident work chunk (0 = default 32768)
       generic_attention force the CUDA-core attention kernels
       fold_ln           bf16 + pre-LN configs: apply norm1 / norm2 inside the QKV / fc1 GEMM epilogues instead of a
                         separate pass (same accuracy; measured neutral on B200 because the residual GEMMs then lose
