@@ -457,6 +457,230 @@ int launch_temporal_t(const AttnArgs& a, int B, int S, int T, int t0, int Tq, vo
   return GN_OK;
 }
 
+
+// =====================================================================================
+// temporal attention v2 (head_dim 64, no qk-LayerNorm): TMA-fed, no per-thread global access.
+// K and V of ALL frames <= the query frame come from a head-major cache [clip*S + s][head][T][64] that the
+// temporal QKV GEMM epilogue writes directly (gemm.cu, kv_* arguments), so one (clip, position) needs exactly
+// three bulk-tensor loads (Q box [Tq][H][64] from the projection output, K and V boxes [H][Tk][64] from the
+// caches) and one bulk-tensor store of the attention output.  Persistent CTAs: warp h < H computes head h
+// (mma.sync m16n8k16, the 16 x 16 causal problem of one position), warp H is the TMA producer running an
+// n_stages-deep mbarrier ring ahead of the consumers.  Key r of a position always sits at tile row r, whatever
+// (t0, Tq) a call uses, so the cached decode stays bit-identical to the dense 16-frame forward.
+// =====================================================================================
+__device__ __forceinline__ uint32_t line_off(int line, int c) {      // SWIZZLE_128B, region base aligned to 1024 B
+  return (uint32_t)(line * 128 + ((c ^ (line & 7)) << 4));
+}
+
+__global__ void __launch_bounds__(576, 1)
+temporal_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, int n_pos,
+                        int S, int H, int t0, int Tq, int n_stages, int rq_bytes, int rk_bytes, float scale_log2e) {
+  constexpr int HD = 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = rq_bytes + 2 * rk_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + n_stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + n_stages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Tk = t0 + Tq;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmO);
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], H);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  pdl_trigger();
+
+  const int n_my = ((int)blockIdx.x < n_pos) ? (n_pos - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (warp == H) {
+    // ------------------------------------------------------------------ TMA producer (one thread)
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)(Tq + 2 * Tk) * H * (HD * 2);
+      auto issue = [&](int j, int st) {
+        const int pos = blockIdx.x + j * gridDim.x;
+        const int b = pos / S, sp = pos - b * S;
+        uint8_t* base = smem + st * stage_bytes;
+        mbar_arrive_expect_tx(&full_bar[st], tx);
+        tma_load_4d(base, &tmQ, &full_bar[st], 0, 0, sp, b * Tq);
+        tma_load_3d(base + rq_bytes, &tmK, &full_bar[st], 0, 0, pos * H);
+        tma_load_3d(base + rq_bytes + rk_bytes, &tmV, &full_bar[st], 0, 0, pos * H);
+      };
+      for (int j = 0; j < n_stages && j < n_my; ++j) issue(j, j);
+      int st = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < n_my; ++j) {
+        mbar_wait(&empty_bar[st], ph);            // every head's output rows are staged in the Q region
+        const int pos = blockIdx.x + j * gridDim.x;
+        const int b = pos / S, sp = pos - b * S;
+        tma_store_4d(&tmO, smem + st * stage_bytes, 0, 0, sp, b * Tq);
+        tma_store_commit();
+        if (j + n_stages < n_my) {
+          tma_store_wait_read<0>();               // the store has read the stage: refill it
+          issue(j + n_stages, st);
+        }
+        if (++st == n_stages) { st = 0; ph ^= 1; }
+      }
+      tma_store_wait_all<0>();
+    }
+  } else {
+    // ------------------------------------------------------------------ one head per warp
+    const int h = warp;
+    const int mi = lane >> 3, l8 = lane & 7;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int qrow = min(l8 + (mi & 1) * 8, Tq - 1);          // rows past the real ones re-read the last real row
+    const int krow = min((mi >> 1) * 8 + l8, Tk - 1);
+    const int vrow = min((mi & 1) * 8 + l8, Tk - 1);
+    uint32_t qo[HD / 16], ko[HD / 16], vo[HD / 16];
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) {
+      qo[kk] = line_off(qrow * H + h, 2 * kk + (mi >> 1));
+      ko[kk] = line_off(h * Tk + krow, 2 * kk + (mi & 1));
+      vo[kk] = line_off(h * Tk + vrow, 2 * kk + (mi >> 1));
+    }
+    int st = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < n_my; ++j) {
+      uint8_t* base = smem + st * stage_bytes;
+      const uint32_t sQa = smem_u32(base), sKa = sQa + rq_bytes, sVa = sKa + rk_bytes;
+      mbar_wait(&full_bar[st], ph);
+      float s[2][4];
+      s[0][0] = s[0][1] = s[0][2] = s[0][3] = 0.f;
+      s[1][0] = s[1][1] = s[1][2] = s[1][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < HD / 16; ++kk) {
+        uint32_t qf[4], kf[4];
+        ldsm_x4(qf, sQa + qo[kk]);
+        ldsm_x4(kf, sKa + ko[kk]);
+        mma_16816(s[0], qf, kf[0], kf[1]);
+        mma_16816(s[1], qf, kf[2], kf[3]);
+      }
+      // causal mask: query row i (frame t0 + i) sees keys j <= t0 + i   (attention.py:51-55)
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = jj * 8 + 2 * t4 + e;
+          if (key > t0 + g) s[jj][e] = -INFINITY;
+          if (key > t0 + g + 8) s[jj][2 + e] = -INFINITY;
+          mx0 = fmaxf(mx0, s[jj][e]);
+          mx1 = fmaxf(mx1, s[jj][2 + e]);
+        }
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          s[jj][e] = exp2f((s[jj][e] - mx0) * scale_log2e);
+          s[jj][2 + e] = exp2f((s[jj][2 + e] - mx1) * scale_log2e);
+          l0 += s[jj][e];
+          l1 += s[jj][2 + e];
+        }
+      }
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      const float i0 = 1.f / l0, i1 = 1.f / l1;
+      uint32_t pa[4];
+      pa[0] = pack_bf16x2(s[0][0], s[0][1]);
+      pa[1] = pack_bf16x2(s[0][2], s[0][3]);
+      pa[2] = pack_bf16x2(s[1][0], s[1][1]);
+      pa[3] = pack_bf16x2(s[1][2], s[1][3]);
+      float o[HD / 8][4];
+#pragma unroll
+      for (int jp = 0; jp < HD / 16; ++jp) {
+        uint32_t vf[4];
+        ldsm_x4_t(vf, sVa + vo[jp]);
+        o[2 * jp][0] = o[2 * jp][1] = o[2 * jp][2] = o[2 * jp][3] = 0.f;
+        o[2 * jp + 1][0] = o[2 * jp + 1][1] = o[2 * jp + 1][2] = o[2 * jp + 1][3] = 0.f;
+        mma_16816(o[2 * jp], pa, vf[0], vf[1]);
+        mma_16816(o[2 * jp + 1], pa, vf[2], vf[3]);
+      }
+      __syncwarp();        // every lane's Q fragments are in registers: the Q lines of this head become output staging
+      if (g < Tq) {
+#pragma unroll
+        for (int c = 0; c < HD / 8; ++c)
+          *reinterpret_cast<uint32_t*>(base + line_off(g * H + h, c) + t4 * 4) = pack_bf16x2(o[c][0] * i0, o[c][1] * i0);
+      }
+      if (g + 8 < Tq) {
+#pragma unroll
+        for (int c = 0; c < HD / 8; ++c)
+          *reinterpret_cast<uint32_t*>(base + line_off((g + 8) * H + h, c) + t4 * 4) =
+              pack_bf16x2(o[c][2] * i1, o[c][3] * i1);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[st]);
+      if (++st == n_stages) { st = 0; ph ^= 1; }
+    }
+  }
+}
+
+int launch_temporal_v2(const AttnArgs& a, int nb, int S, int T, int t0, int Tq, const void* kc, const void* vc,
+                       cudaStream_t st) {
+  const int H = a.n_heads, HD = 64, d = H * HD, Tk = t0 + Tq;
+  const int n_pos = nb * S;
+  CUtensorMap tmQ, tmK, tmV, tmO;
+  {
+    const int64_t dims[4] = {HD, H, S, (int64_t)nb * Tq};
+    const int64_t sq[3] = {HD * 2, (int64_t)3 * d * 2, (int64_t)S * 3 * d * 2};
+    const int64_t so[3] = {HD * 2, (int64_t)d * 2, (int64_t)S * d * 2};
+    const int box[4] = {HD, H, 1, Tq};
+    GN_PROPAGATE(make_tensor_map_nd(&tmQ, a.qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, sq, box,
+                                    CU_TENSOR_MAP_SWIZZLE_128B));
+    GN_PROPAGATE(make_tensor_map_nd(&tmO, a.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, so, box,
+                                    CU_TENSOR_MAP_SWIZZLE_128B));
+    const int64_t dk[3] = {HD, T, (int64_t)H * n_pos};
+    const int64_t sk[2] = {HD * 2, (int64_t)T * HD * 2};
+    const int bk[3] = {HD, Tk, H};
+    GN_PROPAGATE(make_tensor_map_nd(&tmK, kc, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dk, sk, bk, CU_TENSOR_MAP_SWIZZLE_128B));
+    GN_PROPAGATE(make_tensor_map_nd(&tmV, vc, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dk, sk, bk, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  const int rq = (Tq * H * HD * 2 + 1023) & ~1023, rk = (Tk * H * HD * 2 + 1023) & ~1023;
+  const int stage = rq + 2 * rk;
+  int per_sm = 2, ns = (108 * 1024) / stage;
+  if (ns < 3) {
+    per_sm = 1;
+    ns = (222 * 1024) / stage;
+  }
+  if (ns > 8) ns = 8;
+  GN_REQUIRE(ns >= 2, "temporal attention v2: a stage of %d bytes does not fit twice in shared memory", stage);
+  const int smem = ns * stage + 1024 + 2 * ns * 8;
+  auto kern = temporal_attn_v2_kernel;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int grid = std::min(n_pos, sms * per_sm);
+  GN_CUDA_CHECK(launch_kernel(PC_TEMPORAL, kern, dim3(grid), dim3((H + 1) * 32), (size_t)smem, st, tmQ, tmK, tmV, tmO,
+                              n_pos, S, H, t0, Tq, ns, rq, rk, a.scale * 1.4426950408889634f));
+  ++g_launch_count;
+  return GN_OK;
+}
 }  // namespace
 
 bool fast_spatial_supported(const AttnArgs& a, int S) {
@@ -476,6 +700,17 @@ int fast_temporal_attention(const AttnArgs& a, int B, int S, int T, int t0, int 
 
 int generic_temporal_attention(const AttnArgs& a, int B, int S, int T, int t0, int Tq, void* kcache, void* vcache,
                                cudaStream_t st);
+
+bool temporal_v2_supported(const AttnArgs& a, int S, int T) {
+  return a.act_bf16 && a.head_dim == 64 && a.n_heads <= 16 && T <= 16 && S % 32 == 0 && a.qk_gamma == nullptr;
+}
+int launch_temporal_attention_v2(const AttnArgs& a, int nb, int S, int T, int t0, int Tq, const void* kcache,
+                                 const void* vcache, cudaStream_t st) {
+  GN_REQUIRE(temporal_v2_supported(a, S, T), "temporal attention v2: unsupported shape");
+  GN_REQUIRE(t0 >= 0 && Tq >= 1 && t0 + Tq <= T, "temporal attention: bad frame range t0=%d Tq=%d T=%d", t0, Tq, T);
+  GN_REQUIRE(kcache && vcache, "temporal attention v2 reads K/V from the head-major caches");
+  return launch_temporal_v2(a, nb, S, T, t0, Tq, kcache, vcache, st);
+}
 
 int launch_spatial_attention(const AttnArgs& a, int n_frames, int S, int force_generic, cudaStream_t st) {
   if (!force_generic && fast_spatial_supported(a, S)) return fast_spatial_attention(a, n_frames, S, st);

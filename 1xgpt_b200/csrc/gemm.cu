@@ -28,14 +28,15 @@ constexpr int MAX_EPI_WARPS = 8;
 constexpr int MAX_GEMM_THREADS = 32 * (2 + MAX_EPI_WARPS);
 constexpr int SMEM_LIMIT = 232448;           // 227 KB opt-in dynamic shared memory per CTA
 
-constexpr int RES_BUFS = 4;      // residual epilogue: in-place staging buffers per warp
-constexpr int RES_PREFETCH = 2;  // residual chunks requested ahead of use
+constexpr int RES_BUFS = 4;      // residual epilogue: in-place staging buffers per warp (3 for 256-wide tiles that also
+                                 // emit the bf16 copy, so that a 3-stage operand ring still fits)
+constexpr int res_bufs(int block_n, bool dual) { return (block_n > 128 && dual) ? 3 : RES_BUFS; }
 
 template <int BLOCK_N, int EPI, typename OutT, bool DUAL>
 struct GemmSmem {
   static constexpr int NUM_EPI_WARPS = EpiCfg<EPI>::WARPS;
   static constexpr int COLS_PER_WARP = BLOCK_N / (NUM_EPI_WARPS / 4);   // columns of the tile one warp handles
-  static constexpr int OUT_BUFS = EPI == EPI_RESID ? RES_BUFS : (NUM_EPI_WARPS == 8 ? 1 : 2);
+  static constexpr int OUT_BUFS = EPI == EPI_RESID ? res_bufs(BLOCK_N, DUAL) : (NUM_EPI_WARPS == 8 ? 1 : 2);
   static constexpr int B_TILE_BYTES = BLOCK_N * TILE_K_BYTES;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int OUT_STAGE_BYTES = 32 * EPI_COLS * (int)sizeof(OutT);          // per warp per buffer
@@ -64,6 +65,8 @@ struct TcArgs {
   int ln_np, ln_d;
   const float* ln_colsum;
   float* stats_out;
+  // K/V columns of the temporal QKV projection go to the caches (kv_d == 0: off)
+  int kv_d, kv_hd, kv_S, kv_Tact, kv_t0;
 };
 
 template <typename OutT>
@@ -98,7 +101,8 @@ template <typename InT, int BLOCK_N, int EPI, typename OutT, bool DUAL>
 __global__ void __launch_bounds__(32 * (2 + EpiCfg<EPI>::WARPS), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
-                    const __grid_constant__ CUtensorMap tmRes, const TcArgs args) {
+                    const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const TcArgs args) {
   using SM = GemmSmem<BLOCK_N, EPI, OutT, DUAL>;
   constexpr int NUM_EPI_WARPS = SM::NUM_EPI_WARPS;
   constexpr int STAGES = SM::STAGES;
@@ -276,19 +280,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // Residual epilogue.  The fp32 residual chunk (32 rows x 32 cols of this warp) is TMA-loaded into a
       // swizzled staging buffer RES_PREFETCH chunks ahead, updated IN PLACE with acc + bias, and TMA-stored
       // from the same buffer: every global access of the epilogue is a coalesced bulk copy.
+      constexpr int RB = SM::OUT_BUFS;   // staging buffers per warp
+      constexpr int RP = RB - 2;         // residual chunks requested ahead of use
       uint64_t* rbar = res_bar + ew * RES_BUFS;
       const int my_tiles = (int)blockIdx.x < num_tiles ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
       const int total_chunks = my_tiles * CH;
       auto issue_residual = [&](int g) {           // lane 0 only
         const int t = blockIdx.x + (g / CH) * gridDim.x;
         const int mb = t / num_n, nb = t % num_n;
-        const int b = g % RES_BUFS;
+        const int b = g % RB;
         mbar_arrive_expect_tx(&rbar[b], SM::OUT_STAGE_BYTES);
         tma_load_2d(st0 + b * SM::OUT_STAGE_BYTES, &tmRes, &rbar[b], nb * BLOCK_N + (g % CH) * EPI_COLS,
                     mb * BLOCK_M + q * 32);
       };
       if (lane == 0) {
-        for (int g0 = 0; g0 < RES_PREFETCH && g0 < total_chunks; ++g0) issue_residual(g0);
+        for (int g0 = 0; g0 < RP && g0 < total_chunks; ++g0) issue_residual(g0);
       }
       int g = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -302,9 +308,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int c = 0; c < CH; ++c, ++g) {
           const int col0 = n_blk * BLOCK_N + c * EPI_COLS;
           if (lane == 0) {
-            // buffer (g + PREFETCH) % BUFS was last stored from RES_BUFS - RES_PREFETCH chunks ago
-            tma_store_wait_read<RES_BUFS - RES_PREFETCH - 1>();
-            if (g + RES_PREFETCH < total_chunks) issue_residual(g + RES_PREFETCH);
+            // buffer (g + RP) % RB was last stored from RB - RP chunks ago
+            tma_store_wait_read<RB - RP - 1>();
+            if (g + RP < total_chunks) issue_residual(g + RP);
           }
           uint32_t r[EPI_COLS];
           tmem_ld_32x32b_x32(tmem_base + ((q * 32u) << 16) + as * BLOCK_N + c * EPI_COLS, r);
@@ -318,8 +324,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int j = 0; j < EPI_COLS; ++j) v[j] = __uint_as_float(r[j]);
           add_bias(v, c);
-          const int b = g % RES_BUFS;
-          mbar_wait(&rbar[b], (g / RES_BUFS) & 1);
+          const int b = g % RB;
+          mbar_wait(&rbar[b], (g / RB) & 1);
           __syncwarp();                             // lane 0's wait_read above precedes every lane's staging writes
           uint8_t* rowp = st0 + b * SM::OUT_STAGE_BYTES + lane * 128;
 #pragma unroll
@@ -357,6 +363,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(&acc_full[as], aphase);
         tc_fence_after();
         const uint32_t acc_addr = tmem_base + ((q * 32u) << 16) + as * BLOCK_N + col_base;
+        // K/V-cache destination of this warp's 32 rows (rows are (clip, local frame, s); 32 | S)
+        int kv_frame = 0, kv_pos = 0;
+        if (EPI == EPI_STORE && sizeof(OutT) == 2 && args.kv_d > 0) {
+          const int bt = row0 / args.kv_S;
+          kv_frame = args.kv_t0 + bt % args.kv_Tact;
+          kv_pos = (bt / args.kv_Tact) * args.kv_S + row0 % args.kv_S;
+        }
         uint32_t rr[2][EPI_COLS];
         tmem_ld_32x32b_x32(acc_addr, rr[0]);
         // one chunk: wait for its TMEM load, start the next chunk's load (overlaps the math), bias / activation,
@@ -395,7 +408,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmOut, st0 + buf * SM::OUT_STAGE_BYTES, col0, row0);
+            if (EPI == EPI_STORE && sizeof(OutT) == 2 && args.kv_d > 0 && col0 >= args.kv_d) {
+              const int part = col0 >= 2 * args.kv_d ? 2 : 1;
+              const int cc = col0 - part * args.kv_d;
+              tma_store_4d(part == 1 ? &tmK : &tmV, st0 + buf * SM::OUT_STAGE_BYTES, cc % args.kv_hd, kv_frame,
+                           cc / args.kv_hd, kv_pos);
+            } else {
+              tma_store_2d(&tmOut, st0 + buf * SM::OUT_STAGE_BYTES, col0, row0);
+            }
             tma_store_commit();
           }
           if (SM::OUT_BUFS > 1) buf ^= 1;
@@ -426,7 +446,7 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
   const CUtensorMapDataType in_dt = sizeof(InT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   const CUtensorMapDataType out_dt =
       sizeof(OutT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  CUtensorMap tmA, tmB, tmO, tmO2, tmR;
+  CUtensorMap tmA, tmB, tmO, tmO2, tmR, tmK, tmV;
   int tw = 0, th = 0;
   if (a.conv) {
     const ConvGeom& g = *a.conv;
@@ -453,6 +473,21 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
   } else {
     tmR = tmO;
   }
+  const bool kv = EPI == EPI_STORE && sizeof(OutT) == 2 && a.kv_k != nullptr;
+  if (kv) {
+    // cache view [clip*S + s][head][T][hd]; one store = 32 positions x 32 columns of one head and frame
+    const int H = a.kv_d / a.kv_hd;
+    const int64_t dims[4] = {a.kv_hd, a.kv_T, H, (int64_t)a.kv_clips * a.kv_S};
+    const int64_t str[3] = {(int64_t)a.kv_hd * 2, (int64_t)a.kv_T * a.kv_hd * 2, (int64_t)H * a.kv_T * a.kv_hd * 2};
+    const int box[4] = {EPI_COLS, 1, 1, 32};
+    GN_PROPAGATE(make_tensor_map_nd(&tmK, a.kv_k, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, str, box,
+                                    CU_TENSOR_MAP_SWIZZLE_64B));
+    GN_PROPAGATE(make_tensor_map_nd(&tmV, a.kv_v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, str, box,
+                                    CU_TENSOR_MAP_SWIZZLE_64B));
+  } else {
+    tmK = tmO;
+    tmV = tmO;
+  }
   auto kern = gemm_tcgen05_kernel<InT, BLOCK_N, EPI, OutT, DUAL>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -466,7 +501,9 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
   if (!cached_sms) cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev);
   sms = cached_sms > 0 ? cached_sms : 148;
   const int grid = num_tiles < sms ? num_tiles : sms;
-  TcArgs t{a.M, a.N, a.K, a.bias, a.resid, a.ldr, a.round_out_tf32, 0, 0, 0, 0, 0, 1, nullptr, 0, 0, nullptr, nullptr};
+  TcArgs t{a.M, a.N, a.K, a.bias, a.resid, a.ldr, a.round_out_tf32, 0, 0, 0, 0, 0, 1, nullptr, 0, 0, nullptr, nullptr,
+           0, 0, 0, 0, 0};
+  if (kv) { t.kv_d = a.kv_d; t.kv_hd = a.kv_hd; t.kv_S = a.kv_S; t.kv_Tact = a.kv_Tact; t.kv_t0 = a.kv_t0; }
   if (a.conv) {
     t.cin_blocks = a.conv->Cin / BLOCK_K;
     t.Ho = a.conv->Ho; t.Wo = a.conv->Wo; t.tw = tw; t.th = th; t.stride = a.conv->stride;
@@ -474,7 +511,7 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
   t.ln_stats = a.ln_stats; t.ln_np = a.ln_np; t.ln_d = a.ln_d; t.ln_colsum = a.ln_colsum; t.stats_out = a.stats_out;
   g_gemm_flops_issued += 2.0 * a.M * (double)a.N * a.K;
   const int cat = EPI == EPI_RESID ? PC_GEMM_RESID : (EPI == EPI_GELU ? PC_GEMM_GELU : PC_GEMM_STORE);
-  GN_CUDA_CHECK(launch_kernel(cat, kern, dim3(grid), dim3(32 * (2 + SM::NUM_EPI_WARPS)), SM::TOTAL, stream, tmA, tmB, tmO, tmO2, tmR, t));
+  GN_CUDA_CHECK(launch_kernel(cat, kern, dim3(grid), dim3(32 * (2 + SM::NUM_EPI_WARPS)), SM::TOTAL, stream, tmA, tmB, tmO, tmO2, tmR, tmK, tmV, t));
   ++g_launch_count;
   return GN_OK;
 }
@@ -494,9 +531,9 @@ int dispatch_epi(const LinearArgs& a, cudaStream_t s) {
     if constexpr (BLOCK_N <= 128) {
       return a.out2 ? launch_tc<InT, BLOCK_N, EPI_RESID, float, true>(a, s)
                     : launch_tc<InT, BLOCK_N, EPI_RESID, float, false>(a, s);
-    } else {
-      if (a.out2) { set_error("EPI_RESID with a bf16 copy is tiled with BLOCK_N <= 128"); return GN_ERR_INVALID; }
-      return launch_tc<InT, BLOCK_N, EPI_RESID, float, false>(a, s);
+    } else {   // 256-wide: 3 residual staging buffers when the bf16 copy is emitted too
+      return a.out2 ? launch_tc<InT, BLOCK_N, EPI_RESID, float, true>(a, s)
+                    : launch_tc<InT, BLOCK_N, EPI_RESID, float, false>(a, s);
     }
   }
   set_error("unknown epilogue %d", a.epi);
@@ -509,7 +546,7 @@ int dispatch_n(const LinearArgs& a, cudaStream_t s) {
   // Residual epilogues stage 4 fp32 buffers per warp, so they normally take BLOCK_N = 128 to keep a deep TMA ring;
   // for long-K residual GEMMs (fc2: K = 4d) the 128-wide tile is operand-bandwidth bound (A+B = 128 B/clk of smem
   // reads per MMA cycle), so those use 256 with a 3-stage ring.
-  if (a.N % 256 == 0 && (a.epi != EPI_RESID || (a.K >= 1024 && !a.out2))) return dispatch_epi<InT, 256>(a, s);
+  if (a.N % 256 == 0 && (a.epi != EPI_RESID || a.K >= 1024)) return dispatch_epi<InT, 256>(a, s);
   if (a.N % 128 == 0) return dispatch_epi<InT, 128>(a, s);
   return dispatch_epi<InT, 64>(a, s);
 }
@@ -581,7 +618,7 @@ int launch_simt(const LinearArgs& a, cudaStream_t s) {
 }  // namespace
 
 int resid_block_n(int N, int K, bool dual) {
-  if (N % 256 == 0 && K >= 1024 && !dual) return 256;
+  if (N % 256 == 0 && K >= 1024) return 256;
   if (N % 128 == 0) return 128;
   return 64;
 }
@@ -608,6 +645,13 @@ int linear_forward(const LinearArgs& a, cudaStream_t stream) {
     GN_REQUIRE(g.Wo >= 128 || g.Ho % (128 / g.Wo) == 0, "conv: Ho not a multiple of the tile height");
     GN_REQUIRE((g.Wo < 128 ? g.Wo : 128) * g.stride <= 256, "conv: TMA box too wide");
   }
+  if (a.kv_k) {
+    GN_REQUIRE(a.kv_v && a.epi == EPI_STORE && a.in_bf16 && a.out_bf16 && !a.force_simt && !a.conv,
+               "K/V-cache output needs the bf16 tensor path with the store epilogue");
+    GN_REQUIRE(a.kv_d > 0 && a.N == 3 * a.kv_d && a.kv_hd % EPI_COLS == 0 && a.kv_d % a.kv_hd == 0 && a.kv_S % 32 == 0 &&
+                   a.kv_Tact > 0 && a.kv_t0 >= 0 && a.kv_t0 + a.kv_Tact <= a.kv_T && a.M == a.kv_clips * a.kv_Tact * a.kv_S,
+               "K/V-cache output: inconsistent geometry");
+  }
   const bool tc_ok = !a.force_simt && (a.N % 64 == 0) && (a.K * esz % 16 == 0) && (a.lda * esz % 16 == 0) &&
                      (a.ldw * esz % 16 == 0) && (a.ldo * (a.out_bf16 ? 2 : 4) % 16 == 0) &&
                      (!a.out2 || a.ldo2 * 2 % 16 == 0) && (!a.resid || a.ldr * 4 % 16 == 0) &&
@@ -618,6 +662,7 @@ int linear_forward(const LinearArgs& a, cudaStream_t stream) {
                      (!a.bias || reinterpret_cast<uintptr_t>(a.bias) % 16 == 0) &&
                      !(a.out2 && (a.epi != EPI_RESID || a.out_bf16));
   if (tc_ok) return a.in_bf16 ? dispatch_n<bf16>(a, stream) : dispatch_n<float>(a, stream);
+  GN_REQUIRE(!a.kv_k, "K/V-cache output: operands not eligible for the tensor path");
   if (a.in_bf16)
     return a.out_bf16 ? launch_simt<bf16, bf16>(a, stream) : launch_simt<bf16, float>(a, stream);
   return a.out_bf16 ? launch_simt<float, bf16>(a, stream) : launch_simt<float, float>(a, stream);

@@ -54,6 +54,12 @@ struct LinearArgs {
   const float* ln_colsum; // [N]
   // residual epilogue: also emit per-row partial statistics of the new residual stream: [M, N/BLOCK_N, 2]
   float* stats_out;
+  // temporal QKV projection (EPI_STORE, bf16 out, N = 3*kv_d): output columns [kv_d, 2*kv_d) / [2*kv_d, 3*kv_d) are
+  // written straight into the temporal K / V caches (layout [clip*S + s][head][T][hd]) instead of `out`;
+  // GEMM row (b, tl, s) = (b*kv_Tact + tl)*kv_S + s goes to frame kv_t0 + tl.  kv_k == nullptr: off.
+  void* kv_k;
+  void* kv_v;
+  int kv_d, kv_hd, kv_T, kv_S, kv_Tact, kv_t0, kv_clips;
 };
 
 // Enqueue on `stream`.  Returns GN_OK or a negative code (message via last_error()).

@@ -41,6 +41,11 @@ int launch_spatial_attention(const AttnArgs& a, int n_frames, int S, int force_g
 // fresh k/v are written back to the caches when they are non-null.  causal.
 int launch_temporal_attention(const AttnArgs& a, int B, int S, int T, int t0, int Tq, void* kcache, void* vcache,
                               int force_generic, cudaStream_t st);
+// temporal v2 (bf16, head_dim 64, no qk-LayerNorm): K/V of frames [0, t0+Tq) are read from head-major caches
+// [clip*S + s][head][T][64] which the temporal QKV GEMM has already filled (LinearArgs::kv_*); `a.qkv` supplies Q only.
+bool temporal_v2_supported(const AttnArgs& a, int S, int T);
+int launch_temporal_attention_v2(const AttnArgs& a, int nb, int S, int T, int t0, int Tq, const void* kcache,
+                                 const void* vcache, cudaStream_t st);
 // generic standalone attention over [n_seq, n_tok] (SelfAttention.forward contract, any small shape)
 int launch_generic_attention(const AttnArgs& a, int n_seq, int n_tok, int causal, cudaStream_t st);
 

@@ -4,6 +4,7 @@
 #include "kernels.cuh"
 #include "../../include/genie_b200.h"
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <set>
@@ -60,12 +61,16 @@ struct gn_model {
   void* big = nullptr;    // [n, max(3d, hid)] act (qkv / mlp hidden)
   void* o = nullptr;      // [n, d] act
   float* stats = nullptr; // [n, d/64, 2] row-statistics partials for the folded LayerNorm
+  int tv2 = 0;            // temporal attention v2: head-major K/V caches written by the temporal QKV GEMM epilogue
+  void* scr_k = nullptr;  // [chunk clips * S][H][T][hd] scratch K/V for tv2 when the persistent cache is off
+  void* scr_v = nullptr;
   int fold = 0;           // folded-LayerNorm path active (bf16, qk_norm = 0, cfg.fold_ln)
   bool fold_dirty = true;
   int64_t rows_cap = 0;
   float* rows = nullptr;  // [rows_cap, C] fp32 logits rows
 
-  // temporal K/V cache [L][cache_B][S][T][d] act (all frames of one spatial position contiguous)
+  // temporal K/V cache [L][cache_B][S][T][d] act (all frames of one spatial position contiguous);
+  // with tv2 the per-position block is head-major instead: [L][cache_B][S][H][T][hd]
   int cache_B = 0;
   void* kcache = nullptr;
   void* vcache = nullptr;
@@ -119,12 +124,18 @@ int ensure_workspace(gn_model* m, int64_t n) {
   const int d = m->cfg.d_model;
   const int64_t wide = std::max<int64_t>(3 * d, m->hid);
   dev_free(m, m->x); dev_free(m, m->a); dev_free(m, m->big); dev_free(m, m->o); dev_free(m, m->stats);
+  dev_free(m, m->scr_k); dev_free(m, m->scr_v);
+  m->x = nullptr; m->a = m->big = m->o = m->scr_k = m->scr_v = nullptr; m->stats = nullptr;
   m->ws_tokens = 0;
   GN_PROPAGATE(dev_alloc(m, (void**)&m->x, (size_t)n * d * 4));
   GN_PROPAGATE(dev_alloc(m, &m->a, (size_t)n * d * m->esz()));
   GN_PROPAGATE(dev_alloc(m, &m->big, (size_t)n * wide * m->esz()));
   GN_PROPAGATE(dev_alloc(m, &m->o, (size_t)n * d * m->esz()));
   GN_PROPAGATE(dev_alloc(m, (void**)&m->stats, (size_t)n * (d / 64 + 1) * 2 * sizeof(float)));
+  if (m->tv2) {   // dense (cache-less) calls are possible on any handle (compute_logits, forward)
+    GN_PROPAGATE(dev_alloc(m, &m->scr_k, (size_t)n * d * m->esz()));
+    GN_PROPAGATE(dev_alloc(m, &m->scr_v, (size_t)n * d * m->esz()));
+  }
   m->ws_tokens = n;
   return GN_OK;
 }
@@ -171,6 +182,12 @@ int chunk_clips_for(const gn_model* m, int Tact) {
   return c < 1 ? 1 : c;
 }
 
+struct KvOut {   // temporal QKV projection: K/V columns go straight to the (head-major) caches
+  void* k = nullptr;
+  void* v = nullptr;
+  int t0 = 0, Tact = 0, clips = 0;
+};
+
 struct LnFold {
   const float* stats = nullptr;   // consumer: row-statistics partials
   int np = 0;
@@ -180,8 +197,12 @@ struct LnFold {
 
 int linear(gn_model* m, const void* A, int64_t lda, const void* W, int K, const float* bias, const float* resid,
            void* out, int64_t ldo, void* out2, int M, int N, int epi, int out_bf16, cudaStream_t st,
-           const LnFold* lf = nullptr) {
+           const LnFold* lf = nullptr, const KvOut* kv = nullptr) {
   LinearArgs la{};
+  if (kv && kv->k) {
+    la.kv_k = kv->k; la.kv_v = kv->v; la.kv_d = m->cfg.d_model; la.kv_hd = m->cfg.d_model / m->cfg.num_heads;
+    la.kv_T = m->cfg.T; la.kv_S = m->cfg.S; la.kv_Tact = kv->Tact; la.kv_t0 = kv->t0; la.kv_clips = kv->clips;
+  }
   if (lf) {
     la.ln_stats = lf->stats; la.ln_np = lf->np; la.ln_d = m->cfg.d_model; la.ln_colsum = lf->colsum;
     la.stats_out = lf->stats_out;
@@ -193,6 +214,41 @@ int linear(gn_model* m, const void* A, int64_t lda, const void* W, int K, const 
   la.round_out_tf32 = (m->tf32 && epi == EPI_GELU) ? 1 : 0;
   m->flops_executed += 2.0 * M * (double)N * K;
   return linear_forward(la, st);
+}
+
+// temporal QKV projection + causal attention over the frames of each spatial position (st_transformer.py:77-78,
+// attention.py:36-61) for layer l: input rows `ain` [n, d], output m->o.
+int temporal_block(gn_model* m, int l, const void* ain, AttnArgs aa, int b0, int nb, int t0, int Tact, bool use_cache,
+                   cudaStream_t st) {
+  const gn_config& c = m->cfg;
+  const int d = c.d_model, S = c.S, T = c.T;
+  const int n = nb * Tact * S;
+  const int bf = m->act_bf16;
+  const AttnW& w = m->layers[l].attn[1];
+  void *kc = nullptr, *vc = nullptr;
+  if (use_cache) {
+    const size_t layer_stride = (size_t)m->cache_B * T * S * d * m->esz();
+    const size_t clip_off = (size_t)b0 * T * S * d * m->esz();
+    kc = (char*)m->kcache + l * layer_stride + clip_off;
+    vc = (char*)m->vcache + l * layer_stride + clip_off;
+  }
+  if (m->tv2) {
+    if (!use_cache) {
+      GN_REQUIRE(t0 == 0 && Tact == T, "temporal attention without the K/V cache needs the full window");
+      kc = m->scr_k;
+      vc = m->scr_v;
+    }
+    KvOut kv;
+    kv.k = kc; kv.v = vc; kv.t0 = t0; kv.Tact = Tact; kv.clips = nb;
+    GN_PROPAGATE(linear(m, ain, d, w.qkv_w, d, w.qkv_b, nullptr, m->big, 3 * d, nullptr, n, 3 * d, EPI_STORE, 1, st,
+                        nullptr, &kv));
+    GN_PROPAGATE(launch_temporal_attention_v2(aa, nb, S, T, t0, Tact, kc, vc, st));
+  } else {
+    GN_PROPAGATE(linear(m, ain, d, w.qkv_w, d, w.qkv_b, nullptr, m->big, 3 * d, nullptr, n, 3 * d, EPI_STORE, bf, st));
+    GN_PROPAGATE(launch_temporal_attention(aa, nb, S, T, t0, Tact, kc, vc, c.generic_attention || !bf, st));
+  }
+  m->flops_executed += 4.0 * (t0 + Tact) * (double)d * n;
+  return GN_OK;
 }
 
 // Runs the L ST blocks on `n = nb*Tact*S` compact rows already present in m->x.
@@ -227,7 +283,8 @@ int run_layers(gn_model* m, int b0, int nb, int t0, int Tact, bool use_cache, cu
     }
     GN_PROPAGATE(launch_prep_stats(m->x, (bf16*)m->a, m->stats, n, d, st));
     int np = 1;
-    const int np_d = d / resid_block_n(d, d, true);
+    const int np_d = d / resid_block_n(d, d, true);          // partials per row written by the proj epilogue
+    const int np_h = d / resid_block_n(d, m->hid, true);     // ... and by the fc2 epilogue
     for (int l = 0; l < c.num_layers; ++l) {
       const LayerW& w = m->layers[l];
       LnFold lf{};
@@ -239,17 +296,7 @@ int run_layers(gn_model* m, int b0, int nb, int t0, int Tact, bool use_cache, cu
       GN_PROPAGATE(launch_spatial_attention(aa, nb * Tact, S, c.generic_attention, st));
       m->flops_executed += 4.0 * S * (double)d * n;
       GN_PROPAGATE(linear(m, m->o, d, w.attn[0].proj_w, d, w.attn[0].proj_b, m->x, m->x, d, m->a, n, d, EPI_RESID, 0, st));
-      GN_PROPAGATE(linear(m, m->a, d, w.attn[1].qkv_w, d, w.attn[1].qkv_b, nullptr, m->big, 3 * d, nullptr, n, 3 * d,
-                          EPI_STORE, 1, st));
-      void *kc = nullptr, *vc = nullptr;
-      if (use_cache) {
-        const size_t layer_stride = (size_t)m->cache_B * T * S * d * m->esz();
-        const size_t clip_off = (size_t)b0 * T * S * d * m->esz();
-        kc = (char*)m->kcache + l * layer_stride + clip_off;
-        vc = (char*)m->vcache + l * layer_stride + clip_off;
-      }
-      GN_PROPAGATE(launch_temporal_attention(aa, nb, S, T, t0, Tact, kc, vc, c.generic_attention, st));
-      m->flops_executed += 4.0 * (t0 + Tact) * (double)d * n;
+      GN_PROPAGATE(temporal_block(m, l, m->a, aa, b0, nb, t0, Tact, use_cache, st));
       LnFold ps{};
       ps.stats_out = m->stats;
       GN_PROPAGATE(linear(m, m->o, d, w.attn[1].proj_w, d, w.attn[1].proj_b, m->x, m->x, d, m->a, n, d, EPI_RESID, 0, st,
@@ -261,7 +308,7 @@ int run_layers(gn_model* m, int b0, int nb, int t0, int Tact, bool use_cache, cu
       const bool last = l + 1 == c.num_layers;
       GN_PROPAGATE(linear(m, m->big, m->hid, w.fc2_w, m->hid, w.fc2_b, m->x, m->x, d, last ? nullptr : m->a, n, d,
                           EPI_RESID, 0, st, last ? nullptr : &ps));
-      np = np_d;
+      np = np_h;
     }
     return GN_OK;
   }
@@ -292,18 +339,8 @@ int run_layers(gn_model* m, int b0, int nb, int t0, int Tact, bool use_cache, cu
                         EPI_RESID, 0, st));
     if (tf) GN_PROPAGATE(launch_prep(m->x, m->a, 0, nullptr, nullptr, n, d, 1.f, S, Tact, -1, st, 1));
     // ---------------- temporal attention (no LayerNorm in front: st_transformer.py:78)
-    GN_PROPAGATE(linear(m, cp ? m->a : (const void*)m->x, d, w.attn[1].qkv_w, d, w.attn[1].qkv_b, nullptr, m->big,
-                        3 * d, nullptr, n, 3 * d, EPI_STORE, bf, st));
     aa.qk_gamma = w.attn[1].norm_g; aa.qk_beta = w.attn[1].norm_b;
-    void *kc = nullptr, *vc = nullptr;
-    if (use_cache) {
-      const size_t layer_stride = (size_t)m->cache_B * T * S * d * m->esz();
-      const size_t clip_off = (size_t)b0 * T * S * d * m->esz();
-      kc = (char*)m->kcache + l * layer_stride + clip_off;
-      vc = (char*)m->vcache + l * layer_stride + clip_off;
-    }
-    GN_PROPAGATE(launch_temporal_attention(aa, nb, S, T, t0, Tact, kc, vc, c.generic_attention || !bf, st));
-    m->flops_executed += 4.0 * (t0 + Tact) * (double)d * n;
+    GN_PROPAGATE(temporal_block(m, l, cp ? m->a : (const void*)m->x, aa, b0, nb, t0, Tact, use_cache, st));
     const bool copy_t = bf && c.qk_norm;
     GN_PROPAGATE(linear(m, m->o, d, w.attn[1].proj_w, d, w.attn[1].proj_b, m->x, m->x, d, copy_t ? m->a : nullptr, n,
                         d, EPI_RESID, 0, st));
@@ -540,6 +577,13 @@ int gn_model_create(gn_model** out, const gn_config* cfg, int device) {
   m->force_simt = cfg->precision == GN_PREC_FP32;
   m->tf32 = cfg->precision == GN_PREC_TF32;
   m->fold = (m->act_bf16 && !cfg->qk_norm && cfg->fold_ln && cfg->d_model % 64 == 0) ? 1 : 0;
+  {
+    const char* e = getenv("GENIE_B200_TEMPORAL_V2");
+    const bool on = !(e && (e[0] == '0' || e[0] == 'n' || e[0] == 'N'));
+    AttnArgs probe{};
+    probe.act_bf16 = m->act_bf16; probe.n_heads = cfg->num_heads; probe.head_dim = cfg->d_model / cfg->num_heads;
+    m->tv2 = (on && !cfg->qk_norm && !cfg->generic_attention && temporal_v2_supported(probe, cfg->S, cfg->T)) ? 1 : 0;
+  }
   m->hid = (int)(cfg->d_model * cfg->mlp_ratio);
   m->C = cfg->num_factored_vocabs * cfg->factored_vocab_size;
   m->layers.resize(cfg->num_layers);

@@ -123,6 +123,18 @@ int make_tensor_map_3d(CUtensorMap* out, const void* base, CUtensorMapDataType d
   return encode(out, base, dt, 3, dims, strides, box, swz);
 }
 
+int make_tensor_map_nd(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int rank, const int64_t* dims,
+                       const int64_t* strides_bytes, const int* box, CUtensorMapSwizzle swz) {
+  cuuint64_t gd[5] = {1, 1, 1, 1, 1}, gs[4] = {0, 0, 0, 0};
+  cuuint32_t bx[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = (cuuint64_t)dims[i];
+    bx[i] = (cuuint32_t)box[i];
+    if (i > 0) gs[i - 1] = (cuuint64_t)strides_bytes[i - 1];
+  }
+  return encode(out, base, dt, rank, gd, gs, bx, swz);
+}
+
 int make_tensor_map_nhwc(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int elem_bytes, int64_t N,
                          int64_t H, int64_t W, int64_t C, int box_c, int box_w, int box_h, int stride_w, int stride_h,
                          CUtensorMapSwizzle swz) {

@@ -21,4 +21,8 @@ int make_tensor_map_nhwc(CUtensorMap* out, const void* base, CUtensorMapDataType
                          int64_t H, int64_t W, int64_t C, int box_c, int box_w, int box_h, int stride_w, int stride_h,
                          CUtensorMapSwizzle swz);
 
+// General tiled map: `rank` dims (innermost first), byte strides for dims 1..rank-1, box per dim.
+int make_tensor_map_nd(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int rank, const int64_t* dims,
+                       const int64_t* strides_bytes, const int* box, CUtensorMapSwizzle swz);
+
 }  // namespace gn

@@ -302,3 +302,39 @@ def test_cuda_graph_replay_is_bit_identical():
         outs[graphs] = runs[0]
     assert torch.equal(outs[False][0], outs[True][0])
     assert torch.equal(outs[False][1], outs[True][1])
+
+
+def test_temporal_v2_matches_legacy_kernel(monkeypatch):
+    """Temporal attention v2 (TMA-fed, K/V written into head-major caches by the QKV GEMM epilogue) against the
+    legacy per-warp cp.async kernel (GENIE_B200_TEMPORAL_V2=0): same mma operands in the same tile positions, so the
+    logits must agree to fp32 summation noise, and cached generation must equal dense generation bit for bit."""
+    z, kw, cfg, sd = _prod_setup("genie138m")
+    ids = torch.from_numpy(z["ids"]).long()
+    B = ids.shape[0]
+    logits = {}
+    for v2 in ("1", "0"):
+        monkeypatch.setenv("GENIE_B200_TEMPORAL_V2", v2)
+        logits[v2] = build_b200_model(kw, sd, precision="bf16").compute_logits(ids.cuda()).cpu()
+    err = rel_fro(logits["1"], logits["0"])
+    print(f"temporal v2 vs legacy: rel {err:.3e}, bit-identical {torch.equal(logits['1'], logits['0'])}")
+    assert err < 1e-5
+    monkeypatch.setenv("GENIE_B200_TEMPORAL_V2", "1")
+    # autoregressive generation of 3 frames: step 0 recomputes 2 frames (Tq = 2), step 1 one frame (Tq = 1)
+    t_prompt = cfg.T - 3
+    noise = torch.stack([O.tie_free_noise(2, B, cfg.S, seed=77 + t) for t in range(3)])
+    outs = []
+    for kv in (False, True):
+        m = build_b200_model(kw, sd, precision="bf16", kv_cache=kv)
+        gen = m.generate(ids[:, :t_prompt].reshape(B, -1).cuda(), None, max_new_tokens=3 * cfg.S, maskgit_steps=2,
+                         temperature=0.0, noise=noise)
+        outs.append(gen.cpu())
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_folded_layernorm_138m():
+    z, kw, cfg, sd = _prod_setup("genie138m")
+    ids = torch.from_numpy(z["ids"]).long()
+    a = build_b200_model(kw, sd, precision="bf16", fold_ln=True).compute_logits(ids.cuda())
+    b = build_b200_model(kw, sd, precision="bf16", fold_ln=False).compute_logits(ids.cuda())
+    print(f"138M fold vs separate LN rel {rel_fro(a, b):.3e}")
+    assert rel_fro(a, b) < 1e-2
