@@ -47,13 +47,13 @@ SIGNATURES = {
     "gn_decoder_forward": (_i, [_vp, _vp, _vp, _i, _vp]),
     "gn_attention_forward": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _vp]),
     "gn_compute_logits": (_i, [_vp, _vp, _i, _vp, _vp]),
-    "gn_maskgit_generate": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp]),
-    "gn_generate": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
-    "gn_generate_host": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp]),
-    "gn_teacher_forced_eval": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "gn_maskgit_generate": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
+    "gn_generate": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp]),
+    "gn_generate_host": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
+    "gn_teacher_forced_eval": (_i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "gn_forward_loss": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "gn_linear_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "gn_sample_tokens": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "gn_sample_tokens": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "gn_remask_step": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "gn_cross_entropy": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "gn_vq_create": (_i, [C.POINTER(_vp), C.POINTER(gn_vq_config), _i]),

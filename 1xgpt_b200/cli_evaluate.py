@@ -45,7 +45,8 @@ def main(argv=None):
     clips = ds.clips()
     model = STMaskGIT.from_pretrained(args.checkpoint_dir, kv_cache=True).to(f"cuda:{local}")
     t0 = time.time()
-    res = evaluate_clips(clips, b200_backend(model, maskgit_steps=args.maskgit_steps, noise_seed=42),
+    res = evaluate_clips(clips, b200_backend(model, maskgit_steps=args.maskgit_steps, noise_seed=42,
+                                              temperature=args.temperature),
                          batch_size=args.batch_size, acc_device=model.device)
     torch.cuda.synchronize()
     res["gen_time"] = (time.time() - t0) / max(1, (WINDOW_SIZE - 1) * res["local_clips"])

@@ -6,15 +6,19 @@
 namespace gn {
 
 // -------------------------------------------------------------------------------------
-// factored softmax -> greedy sample + confidence, one warp per token
-// reference: genie/st_mask_git.py:171-190 (temperature <= 1e-8 branch)
-//   probs = softmax over each 512-way vocab; sample_i = argmax; id = sum_i sample_i * V^i (high vocab first);
-//   conf = prod_i probs_i[sample_i]  (= prod_i 1 / sum_j exp(l_j - max))
-// ties: lowest index (torch.argmax returns the first maximal element)
+// factored softmax -> sample + confidence, one warp per token
+// reference: genie/st_mask_git.py:171-190
+//   probs = softmax over each 512-way vocab; id = sum_i sample_i * V^i (high vocab first);
+//   conf = prod_i probs_i[sample_i]
+//   temperature <= 1e-8 (uniform == nullptr): sample_i = argmax (ties: lowest index, like torch.argmax)
+//   temperature  > 1e-8 (uniform != nullptr): sample_i ~ Categorical(probs_i / temperature).  Categorical
+//     renormalises its `probs` argument, so the temperature cancels and the draw is from softmax(logits_i)
+//     (st_mask_git.py:184-187).  The draw is made by inverse CDF from a caller-supplied uniform u in [0,1):
+//     sample_i = min{ c : sum_{j<=c} e_j > u * sum_j e_j },  e_j = exp(l_j - max)  (index order, fp32).
 // -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-sample_kernel(const float* __restrict__ logits, int R, int V, int NV, int32_t* __restrict__ samples,
-              float* __restrict__ conf) {
+sample_kernel(const float* __restrict__ logits, int R, int V, int NV, const float* __restrict__ uniform,
+              int32_t* __restrict__ samples, float* __restrict__ conf) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= R) return;
   const int lane = threadIdx.x & 31;
@@ -38,8 +42,36 @@ sample_kernel(const float* __restrict__ logits, int R, int V, int NV, int32_t* _
     float sum = 0.f;
     for (int c = lane; c < V; c += 32) sum += expf(l[c] - mx);
     sum = warp_sum(sum);
+    float pe = 1.f;                       // e_sample (greedy: exp(0))
+    if (uniform != nullptr) {
+      const float target = uniform[(int64_t)row * NV + i] * sum;
+      float carry = 0.f;
+      int found = -1;
+      for (int c0 = 0; c0 < V && found < 0; c0 += 32) {
+        const int c = c0 + lane;
+        const float ev = c < V ? expf(l[c] - mx) : 0.f;
+        float sc = ev;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float t = __shfl_up_sync(0xffffffffu, sc, o);
+          if (lane >= o) sc += t;
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, c < V && carry + sc > target);
+        if (hit) {
+          const int src = __ffs(hit) - 1;
+          found = c0 + src;
+          pe = __shfl_sync(0xffffffffu, ev, src);
+        }
+        carry += __shfl_sync(0xffffffffu, sc, 31);
+      }
+      if (found < 0) {                    // u * sum rounded past the last partial sum
+        found = V - 1;
+        pe = expf(l[V - 1] - mx);
+      }
+      arg = found;
+    }
     id = id * V + arg;
-    cf *= 1.f / sum;
+    cf *= pe / sum;
   }
   if (lane == 0) {
     samples[row] = id;
@@ -47,9 +79,10 @@ sample_kernel(const float* __restrict__ logits, int R, int V, int NV, int32_t* _
   }
 }
 
-int launch_sample(const float* logits, int R, int V, int NV, int32_t* samples, float* conf, cudaStream_t st) {
+int launch_sample(const float* logits, int R, int V, int NV, const float* uniform, int32_t* samples, float* conf,
+                  cudaStream_t st) {
   const int wpb = 8;
-  sample_kernel<<<ceil_div(R, wpb), wpb * 32, 0, st>>>(logits, R, V, NV, samples, conf);
+  sample_kernel<<<ceil_div(R, wpb), wpb * 32, 0, st>>>(logits, R, V, NV, uniform, samples, conf);
   GN_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;
   return GN_OK;

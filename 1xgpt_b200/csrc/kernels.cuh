@@ -50,8 +50,10 @@ int launch_temporal_attention_v2(const AttnArgs& a, int nb, int S, int T, int t0
 int launch_generic_attention(const AttnArgs& a, int n_seq, int n_tok, int causal, cudaStream_t st);
 
 // ---- decode.cu
-// factored softmax / argmax / confidence of one frame's logits rows [R, NV*V]  (st_mask_git.py:171-190)
-int launch_sample(const float* logits, int R, int V, int NV, int32_t* samples, float* conf, cudaStream_t st);
+// factored softmax / argmax-or-categorical / confidence of one frame's logits rows [R, NV*V]  (st_mask_git.py:171-190)
+// uniform: nullptr = greedy argmax; else [R, NV] uniforms in [0,1) for the inverse-CDF categorical draw
+int launch_sample(const float* logits, int R, int V, int NV, const float* uniform, int32_t* samples, float* conf,
+                  cudaStream_t st);
 // cosine re-mask + scatter for one MaskGIT step (st_mask_git.py:192-223), one CTA per clip
 int launch_remask(int32_t* prompt_frame, int64_t clip_stride, const int32_t* samples, const float* conf_or_noise,
                   uint8_t* unmasked, int32_t* samples_out, int B, int S, int n_mask, int last_step, int mask_id,

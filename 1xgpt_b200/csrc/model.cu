@@ -462,8 +462,8 @@ __global__ void relevant_weight_kernel(const int32_t* __restrict__ ids, uint8_t*
 // temporal K,V must be (re)computed at step 0 when the K/V cache is on (0 for a stand-alone call).
 // CE hooks: when `ce_targets` != nullptr the step-0 logits are scored against it (evaluate.py:177).
 int maskgit_impl(gn_model* m, int32_t* prompt, int B, int out_t, int steps, int unmask_mode, const float* noise,
-                 int32_t* samples, float* logits0, int logits0_Tout, int logits0_slot, int recompute_from,
-                 const int32_t* ce_targets, double* acc, cudaStream_t st) {
+                 const float* uniform, int32_t* samples, float* logits0, int logits0_Tout, int logits0_slot,
+                 int recompute_from, const int32_t* ce_targets, double* acc, cudaStream_t st) {
   const gn_config& c = m->cfg;
   const int S = c.S, T = c.T;
   GN_PROPAGATE(ensure_decode(m, B));
@@ -489,8 +489,10 @@ int maskgit_impl(gn_model* m, int32_t* prompt, int B, int out_t, int steps, int 
         GN_PROPAGATE(launch_ce(m->logits_frame, ce_targets, (int64_t)T * S, S, B * S, c.factored_vocab_size,
                                c.num_factored_vocabs, nullptr, acc, st));
     }
-    GN_PROPAGATE(launch_sample(m->logits_frame, B * S, c.factored_vocab_size, c.num_factored_vocabs, m->samples_tmp,
-                               m->conf, st));
+    // uniform [steps, B, S, NV]: Categorical draw of this step (st_mask_git.py:182-187); nullptr = argmax
+    const float* un = uniform ? uniform + (int64_t)step * B * S * c.num_factored_vocabs : nullptr;
+    GN_PROPAGATE(launch_sample(m->logits_frame, B * S, c.factored_vocab_size, c.num_factored_vocabs, un,
+                               m->samples_tmp, m->conf, st));
     const bool last = step == steps - 1;
     const int n_mask = last ? 0 : (int)std::ceil(std::cos((step + 1.0) / steps * M_PI / 2.0) * S);
     const float* cf = nullptr;
@@ -501,11 +503,14 @@ int maskgit_impl(gn_model* m, int32_t* prompt, int B, int out_t, int steps, int 
   return GN_OK;
 }
 
-int check_generate_args(gn_model* m, int B, int steps, float temperature, int unmask_mode, const float* noise) {
+int check_generate_args(gn_model* m, int B, int steps, float temperature, int unmask_mode, const float* noise,
+                        const float* uniform) {
   GN_REQUIRE(m != nullptr, "null model handle");
   GN_REQUIRE(B > 0, "batch must be positive (got %d)", B);
   GN_REQUIRE(steps >= 1, "maskgit_steps must be >= 1 (got %d)", steps);
-  GN_REQUIRE(temperature <= 1e-8f, "temperature > 0 (Categorical sampling, st_mask_git.py:182-187) is not implemented");
+  GN_REQUIRE(temperature <= 1e-8f || uniform != nullptr,
+             "temperature > 0 (Categorical sampling, st_mask_git.py:182-187) needs the caller's uniform tensor "
+             "[.., steps, B, S, num_factored_vocabs]");
   GN_REQUIRE(unmask_mode == GN_UNMASK_RANDOM || unmask_mode == GN_UNMASK_GREEDY,
              "Expected `unmask_mode` to be one of ['greedy', 'random'], got %d", unmask_mode);
   GN_REQUIRE(steps == 1 || unmask_mode == GN_UNMASK_GREEDY || noise != nullptr,
@@ -779,8 +784,9 @@ int gn_compute_logits(gn_model* m, const int32_t* ids, int B, float* logits, voi
 }
 
 int gn_maskgit_generate(gn_model* m, int32_t* prompt, int B, int out_t, int steps, float temperature, int unmask_mode,
-                        const float* noise, int32_t* samples, float* logits0, void* stream) {
-  GN_PROPAGATE(check_generate_args(m, B, steps, temperature, unmask_mode, noise));
+                        const float* noise, const float* uniform, int32_t* samples, float* logits0, void* stream) {
+  GN_PROPAGATE(check_generate_args(m, B, steps, temperature, unmask_mode, noise, uniform));
+  if (temperature <= 1e-8f) uniform = nullptr;
   GN_REQUIRE(prompt && samples, "gn_maskgit_generate: null buffer");
   GN_REQUIRE(out_t > 0, "maskgit_generate requires out_t > 0");
   GN_REQUIRE(out_t < m->cfg.T, "out_t %d out of range (T=%d)", out_t, m->cfg.T);
@@ -792,12 +798,14 @@ int gn_maskgit_generate(gn_model* m, int32_t* prompt, int B, int out_t, int step
   // The reference asserts before doing any work (st_mask_git.py:155); we must not mutate the prompt if
   // the precondition fails, so this one check is synchronous, like the reference's.
   GN_PROPAGATE(sync_check_flag(m, out_t, st));
-  return maskgit_impl(m, prompt, B, out_t, steps, unmask_mode, noise, samples, logits0, 1, 0, 0, nullptr, nullptr, st);
+  return maskgit_impl(m, prompt, B, out_t, steps, unmask_mode, noise, uniform, samples, logits0, 1, 0, 0, nullptr,
+                      nullptr, st);
 }
 
 int gn_generate(gn_model* m, int32_t* tokens, int B, int t_prompt, int steps, float temperature, int unmask_mode,
-                const float* noise, float* logits0, void* stream) {
-  GN_PROPAGATE(check_generate_args(m, B, steps, temperature, unmask_mode, noise));
+                const float* noise, const float* uniform, float* logits0, void* stream) {
+  GN_PROPAGATE(check_generate_args(m, B, steps, temperature, unmask_mode, noise, uniform));
+  if (temperature <= 1e-8f) uniform = nullptr;
   GN_REQUIRE(tokens, "gn_generate: null buffer");
   const gn_config& c = m->cfg;
   GN_REQUIRE(t_prompt >= 1 && t_prompt <= c.T, "num_prompt_frames %d out of range [1, %d]", t_prompt, c.T);
@@ -808,15 +816,16 @@ int gn_generate(gn_model* m, int32_t* tokens, int B, int t_prompt, int steps, fl
   const int Tnew = c.T - t_prompt;
   for (int t = t_prompt; t < c.T; ++t) {
     const float* nz = noise ? noise + (int64_t)(t - t_prompt) * (steps - 1) * B * c.S : nullptr;
+    const float* un = uniform ? uniform + (int64_t)(t - t_prompt) * steps * B * c.S * c.num_factored_vocabs : nullptr;
     const int from = (t == t_prompt) ? 0 : t - 1;
-    GN_PROPAGATE(maskgit_impl(m, tokens, B, t, steps, unmask_mode, nz, m->samples_scratch, logits0, Tnew, t - t_prompt,
-                              from, nullptr, nullptr, st));
+    GN_PROPAGATE(maskgit_impl(m, tokens, B, t, steps, unmask_mode, nz, un, m->samples_scratch, logits0, Tnew,
+                              t - t_prompt, from, nullptr, nullptr, st));
   }
   return GN_OK;
 }
 
 int gn_generate_host(gn_model* m, int32_t* tokens_host, int B, int t_prompt, int steps, float temperature,
-                     int unmask_mode, const float* noise_host, void* stream) {
+                     int unmask_mode, const float* noise_host, const float* uniform_host, void* stream) {
   GN_REQUIRE(m && tokens_host && B > 0, "gn_generate_host: invalid argument");
   DeviceGuard g(m->device);
   cudaStream_t st = (cudaStream_t)stream;
@@ -829,24 +838,29 @@ int gn_generate_host(gn_model* m, int32_t* tokens_host, int B, int t_prompt, int
     m->tokens_cap = ntok;
   }
   const int64_t nnoise = noise_host ? (int64_t)(c.T - t_prompt) * (steps - 1) * B * c.S : 0;
-  if (nnoise > m->noise_cap) {
+  const int64_t nuni = (uniform_host && temperature > 1e-8f)
+                           ? (int64_t)(c.T - t_prompt) * steps * B * c.S * c.num_factored_vocabs : 0;
+  if (nnoise + nuni > m->noise_cap) {   // one staging buffer: [noise | uniform]
     dev_free(m, m->noise_dev);
     m->noise_cap = 0;
-    GN_PROPAGATE(dev_alloc(m, (void**)&m->noise_dev, (size_t)nnoise * 4));
-    m->noise_cap = nnoise;
+    GN_PROPAGATE(dev_alloc(m, (void**)&m->noise_dev, (size_t)(nnoise + nuni) * 4));
+    m->noise_cap = nnoise + nuni;
   }
   GN_CUDA_CHECK(cudaMemcpyAsync(m->tokens_dev, tokens_host, (size_t)ntok * 4, cudaMemcpyHostToDevice, st));
   if (nnoise) GN_CUDA_CHECK(cudaMemcpyAsync(m->noise_dev, noise_host, (size_t)nnoise * 4, cudaMemcpyHostToDevice, st));
+  if (nuni)
+    GN_CUDA_CHECK(cudaMemcpyAsync(m->noise_dev + nnoise, uniform_host, (size_t)nuni * 4, cudaMemcpyHostToDevice, st));
   GN_PROPAGATE(gn_generate(m, m->tokens_dev, B, t_prompt, steps, temperature, unmask_mode, nnoise ? m->noise_dev : nullptr,
-                           nullptr, stream));
+                           nuni ? m->noise_dev + nnoise : nullptr, nullptr, stream));
   GN_CUDA_CHECK(cudaMemcpyAsync(tokens_host, m->tokens_dev, (size_t)ntok * 4, cudaMemcpyDeviceToHost, st));
   GN_CUDA_CHECK(cudaStreamSynchronize(st));
   return GN_OK;
 }
 
-int gn_teacher_forced_eval(gn_model* m, const int32_t* gt, int B, int steps, int unmask_mode, const float* noise,
-                           int32_t* samples_out, double* acc, void* stream) {
-  GN_PROPAGATE(check_generate_args(m, B, steps, 0.f, unmask_mode, noise));
+int gn_teacher_forced_eval(gn_model* m, const int32_t* gt, int B, int steps, float temperature, int unmask_mode,
+                           const float* noise, const float* uniform, int32_t* samples_out, double* acc, void* stream) {
+  GN_PROPAGATE(check_generate_args(m, B, steps, temperature, unmask_mode, noise, uniform));
+  if (temperature <= 1e-8f) uniform = nullptr;
   GN_REQUIRE(gt && acc, "gn_teacher_forced_eval: null buffer");
   DeviceGuard g(m->device);
   cudaStream_t st = (cudaStream_t)stream;
@@ -858,8 +872,9 @@ int gn_teacher_forced_eval(gn_model* m, const int32_t* gt, int B, int steps, int
     GN_CUDA_CHECK(cudaMemcpyAsync(m->prompt_scratch, gt, (size_t)B * TS * 4, cudaMemcpyDeviceToDevice, st));
     GN_PROPAGATE(fill_frames(m->prompt_scratch, B, c.T, c.S, t, c.image_vocab_size, st));
     const float* nz = noise ? noise + (int64_t)(t - 1) * (steps - 1) * B * c.S : nullptr;
+    const float* un = uniform ? uniform + (int64_t)(t - 1) * steps * B * c.S * c.num_factored_vocabs : nullptr;
     int32_t* sout = m->samples_scratch;
-    GN_PROPAGATE(maskgit_impl(m, m->prompt_scratch, B, t, steps, unmask_mode, nz, sout, nullptr, 1, 0, t - 1,
+    GN_PROPAGATE(maskgit_impl(m, m->prompt_scratch, B, t, steps, unmask_mode, nz, un, sout, nullptr, 1, 0, t - 1,
                               gt + (int64_t)t * c.S, acc, st));
     GN_PROPAGATE(launch_count_equal(sout, c.S, gt + (int64_t)t * c.S, TS, c.S, B * c.S, acc, st));
     if (samples_out) {
@@ -909,9 +924,10 @@ int gn_linear_forward(const void* a, const void* w, const float* bias, const flo
   return linear_forward(la, (cudaStream_t)stream);
 }
 
-int gn_sample_tokens(const float* logits_rows, int R, int V, int NV, int32_t* samples, float* conf, void* stream) {
+int gn_sample_tokens(const float* logits_rows, int R, int V, int NV, const float* uniform, int32_t* samples,
+                     float* conf, void* stream) {
   GN_REQUIRE(logits_rows && samples && conf && R > 0, "gn_sample_tokens: invalid argument");
-  return launch_sample(logits_rows, R, V, NV, samples, conf, (cudaStream_t)stream);
+  return launch_sample(logits_rows, R, V, NV, uniform, samples, conf, (cudaStream_t)stream);
 }
 int gn_remask_step(int32_t* prompt_frame, int64_t clip_stride, const int32_t* samples, const float* conf_or_noise,
                    uint8_t* unmasked, int32_t* samples_out, int B, int S, int n_mask, int last_step, int mask_id,

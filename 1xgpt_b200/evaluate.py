@@ -62,7 +62,8 @@ def evaluate_clips(clips: torch.Tensor, backend_fn: Callable[[torch.Tensor, int]
     return out
 
 
-def b200_backend(model, maskgit_steps: int = 2, unmask_mode: str = "random", noise_seed: Optional[int] = 1234):
+def b200_backend(model, maskgit_steps: int = 2, unmask_mode: str = "random", noise_seed: Optional[int] = 1234,
+                 temperature: float = 0.0):
     """backend_fn for a 1xgpt_b200.STMaskGIT on this rank's GPU.  MaskGIT re-mask noise (torch.rand_like in the
     reference) is drawn per clip from a generator seeded with (noise_seed + global clip index), so results do
     not depend on how clips are sharded or batched."""
@@ -77,7 +78,14 @@ def b200_backend(model, maskgit_steps: int = 2, unmask_mode: str = "random", noi
                 g = torch.Generator().manual_seed(noise_seed + first_index + i)
                 per_clip.append(torch.rand(cfg.T - 1, maskgit_steps - 1, cfg.S, generator=g))
             noise = torch.stack(per_clip, dim=2)  # [T-1, K-1, B, S]
+        uniform = None
+        if temperature > 1e-8:                    # Categorical draws (evaluate.py --temperature), same per-clip seeding
+            per_clip = []
+            for i in range(B):
+                g = torch.Generator().manual_seed(noise_seed + first_index + i + (1 << 20))
+                per_clip.append(torch.rand(cfg.T - 1, maskgit_steps, cfg.S, cfg.num_factored_vocabs, generator=g))
+            uniform = torch.stack(per_clip, dim=2)  # [T-1, K, B, S, NV]
         return model.teacher_forced_eval(batch.reshape(B, -1), maskgit_steps=maskgit_steps, unmask_mode=unmask_mode,
-                                         noise=noise)
+                                         noise=noise, temperature=temperature, uniform=uniform)
 
     return fn

@@ -332,16 +332,27 @@ class STMaskGIT(nn.Module):
             return None
         return torch.rand(*shape, device=self.device, dtype=torch.float32)
 
+    def _uniform(self, shape, temperature, uniform):
+        """Categorical(probs / temperature).sample() of the reference (st_mask_git.py:184-187) draws from the global
+        torch RNG; here the draw is an inverse CDF over uniforms [..., steps, B, S, NV] that come from the torch
+        generator of the model's device, or from the caller (`uniform=`) for a reproducible run."""
+        if temperature <= 1e-8:
+            return None
+        if uniform is not None:
+            u = uniform.to(device=self.device, dtype=torch.float32).contiguous()
+            if tuple(u.shape) != tuple(shape):
+                raise ValueError(f"uniform must have shape {tuple(shape)}, got {tuple(u.shape)}")
+            return u
+        return torch.rand(*shape, device=self.device, dtype=torch.float32)
+
     @torch.no_grad()
     def maskgit_generate(self, prompt_THW: torch.LongTensor, out_t: int, maskgit_steps: int = 1,
                          temperature: float = 0.0, unmask_mode: str = "random",
-                         noise: Optional[torch.Tensor] = None):
+                         noise: Optional[torch.Tensor] = None, uniform: Optional[torch.Tensor] = None):
         """st_mask_git.py:123-229.  Mutates prompt_THW[:, out_t] in place; returns
         (sample_HW [B,H,W] int64, factored_logits [B, V, NV, H, W] of step 0)."""
         assert out_t, "maskgit_generate requires out_t > 0"
         mode = self._unmask_mode(unmask_mode)
-        if temperature > 1e-8:
-            raise NotImplementedError("temperature > 0 (Categorical sampling) is not implemented on the B200 path")
         h = self._handle()
         c = self.config
         B, T, H, W = prompt_THW.shape
@@ -351,13 +362,14 @@ class STMaskGIT(nn.Module):
         nz = None
         if mode == _lib.GN_UNMASK_RANDOM and maskgit_steps > 1:
             nz = self._noise((maskgit_steps - 1, B, c.S), noise)
+        un = self._uniform((maskgit_steps, B, c.S, c.num_factored_vocabs), temperature, uniform)
         Cc = c.factored_vocab_size * c.num_factored_vocabs
         samples = torch.empty(B, c.S, device=self.device, dtype=torch.int32)
         logits0 = torch.empty(B, Cc, c.S, device=self.device, dtype=torch.float32)
         try:
             _lib.check(h.lib.gn_maskgit_generate(h.ptr, _ptr(ids), B, int(out_t), int(maskgit_steps),
-                                                 float(temperature), mode, _ptr(nz), _ptr(samples), _ptr(logits0),
-                                                 _stream(self.device)))
+                                                 float(temperature), mode, _ptr(nz), _ptr(un), _ptr(samples),
+                                                 _ptr(logits0), _stream(self.device)))
         except _lib.GnError as e:
             if "must be masked" in str(e):
                 raise AssertionError(f"when generating z{out_t}, frames {out_t} and later must be masked") from e
@@ -370,14 +382,13 @@ class STMaskGIT(nn.Module):
     @torch.no_grad()
     def generate(self, input_ids: torch.LongTensor, attention_mask: torch.LongTensor, max_new_tokens: int,
                  min_new_tokens: int = None, return_logits: int = False, maskgit_steps: int = 1,
-                 temperature: float = 0.0, noise: Optional[torch.Tensor] = None):
+                 temperature: float = 0.0, noise: Optional[torch.Tensor] = None,
+                 uniform: Optional[torch.Tensor] = None):
         """st_mask_git.py:65-113 (Llama-style signature; `attention_mask` ignored like the reference)."""
         assert min_new_tokens in (None, max_new_tokens), \
             "Expecting `min_new_tokens`, if specified, to match `max_new_tokens`."
         c = self.config
         assert max_new_tokens % c.S == 0, "Expecting `max_new_tokens` to be a multiple of `self.config.S`."
-        if temperature > 1e-8:
-            raise NotImplementedError("temperature > 0 (Categorical sampling) is not implemented on the B200 path")
         num_new = max_new_tokens // c.S
         B = input_ids.size(0)
         t_prompt = input_ids.size(1) // c.S
@@ -392,8 +403,9 @@ class STMaskGIT(nn.Module):
             nz = self._noise((num_new, maskgit_steps - 1, B, c.S), noise)
         Cc = c.factored_vocab_size * c.num_factored_vocabs
         logits0 = torch.empty(B, Cc, num_new, c.S, device=self.device, dtype=torch.float32) if return_logits else None
+        un = self._uniform((num_new, maskgit_steps, B, c.S, c.num_factored_vocabs), temperature, uniform)
         _lib.check(h.lib.gn_generate(h.ptr, _ptr(tokens), B, t_prompt, int(maskgit_steps), float(temperature),
-                                     _lib.GN_UNMASK_RANDOM, _ptr(nz), _ptr(logits0), _stream(self.device)))
+                                     _lib.GN_UNMASK_RANDOM, _ptr(nz), _ptr(un), _ptr(logits0), _stream(self.device)))
         predicted = tokens.to(torch.long).reshape(B, c.T * c.S)
         if return_logits:
             fl = logits0.reshape(B, c.num_factored_vocabs, c.factored_vocab_size, num_new, self.h, self.w)
@@ -419,7 +431,8 @@ class STMaskGIT(nn.Module):
 
     @torch.no_grad()
     def teacher_forced_eval(self, input_ids: torch.Tensor, maskgit_steps: int = 2, unmask_mode: str = "random",
-                            noise: Optional[torch.Tensor] = None, return_samples: bool = False):
+                            noise: Optional[torch.Tensor] = None, return_samples: bool = False,
+                            temperature: float = 0.0, uniform: Optional[torch.Tensor] = None):
         """evaluate.py:82-122,173-179 fused: returns the accumulator tensor [sum CE, tokens, argmax-correct,
         sample-correct] (float64, device) for this batch, optionally the samples [B, T-1, H, W]."""
         h = self._handle()
@@ -432,8 +445,9 @@ class STMaskGIT(nn.Module):
             nz = self._noise((c.T - 1, maskgit_steps - 1, B, c.S), noise)
         acc = torch.zeros(4, device=self.device, dtype=torch.float64)
         samples = torch.empty(B, c.T - 1, c.S, device=self.device, dtype=torch.int32) if return_samples else None
-        _lib.check(h.lib.gn_teacher_forced_eval(h.ptr, _ptr(gt), B, int(maskgit_steps), mode, _ptr(nz),
-                                                _ptr(samples), _ptr(acc), _stream(self.device)))
+        un = self._uniform((c.T - 1, maskgit_steps, B, c.S, c.num_factored_vocabs), temperature, uniform)
+        _lib.check(h.lib.gn_teacher_forced_eval(h.ptr, _ptr(gt), B, int(maskgit_steps), float(temperature), mode,
+                                                _ptr(nz), _ptr(un), _ptr(samples), _ptr(acc), _stream(self.device)))
         if return_samples:
             return acc, samples.to(torch.long).reshape(B, c.T - 1, self.h, self.w)
         return acc

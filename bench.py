@@ -248,14 +248,14 @@ def main():
     def step_device(mh):
         work.copy_(clips_dev)
         pkg._lib.check(lib.gn_generate(mh.ptr, C.c_void_p(work.data_ptr()), B, T_PROMPT, MASKGIT_STEPS, 0.0, 0,
-                                       C.c_void_p(noise_dev.data_ptr()), None, sptr))
+                                       C.c_void_p(noise_dev.data_ptr()), None, None, sptr))
 
     host_buf = torch.empty_like(clips_pin).pin_memory()
 
     def step_host(mh):
         host_buf.copy_(clips_pin)
         pkg._lib.check(lib.gn_generate_host(mh.ptr, C.c_void_p(host_buf.data_ptr()), B, T_PROMPT, MASKGIT_STEPS, 0.0,
-                                            0, C.c_void_p(noise_pin.data_ptr()), sptr))
+                                            0, C.c_void_p(noise_pin.data_ptr()), None, sptr))
         return int(host_buf[0, T - 1, 0])  # touch the result (already synchronised by the call)
 
     def barrier():

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define GN_ABI_VERSION 1
+#define GN_ABI_VERSION 2
 
 /* precision modes of the linear layers / activations */
 #define GN_PREC_BF16 0 /* tcgen05 kind::f16, bf16 operands+activations, fp32 accumulate/residual/LN/softmax */
@@ -93,26 +93,31 @@ int gn_compute_logits(gn_model* m, const int32_t* ids, int B, float* logits, voi
  *   the device, reported as an error after the call's work is enqueued and the stream synchronised);
  *   noise [steps-1, B, S] fp32 replaces torch.rand_like for GN_UNMASK_RANDOM (required when steps > 1);
  *   samples [B,S] out; logits0 [B, NV*V, S] fp32 out (step-0 logits of frame out_t; nullable).
- *   temperature must be <= 1e-8 (greedy sampling; the Categorical branch is not implemented). */
+ *   temperature <= 1e-8: argmax per factored vocab.  temperature > 1e-8: Categorical(probs / temperature) per
+ *   factored vocab (st_mask_git.py:182-187; Categorical renormalises, so the draw is from softmax(logits) whatever
+ *   the temperature), drawn by inverse CDF from `uniform` [steps, B, S, NV] fp32 in [0,1) (required then; it
+ *   replaces the reference's global torch RNG the way `noise` replaces torch.rand_like). */
 int gn_maskgit_generate(gn_model* m, int32_t* prompt, int B, int out_t, int steps, float temperature, int unmask_mode,
-                        const float* noise, int32_t* samples, float* logits0, void* stream);
+                        const float* noise, const float* uniform, int32_t* samples, float* logits0, void* stream);
 
 /* genie/generate.py:77-103 / STMaskGIT.generate (st_mask_git.py:65-113): autoregressively fill frames
  * t_prompt..T-1 of tokens [B,T,S] (frames >= t_prompt are overwritten with mask first).
- *   noise [T-t_prompt, steps-1, B, S];  logits0 [B, NV*V, T-t_prompt, S] nullable. */
+ *   noise [T-t_prompt, steps-1, B, S];  uniform [T-t_prompt, steps, B, S, NV] (temperature > 1e-8 only, else
+ *   nullable);  logits0 [B, NV*V, T-t_prompt, S] nullable. */
 int gn_generate(gn_model* m, int32_t* tokens, int B, int t_prompt, int steps, float temperature, int unmask_mode,
-                const float* noise, float* logits0, void* stream);
-/* same, host buffers (pageable or pinned): H2D of tokens(+noise), D2H of tokens inside the call */
+                const float* noise, const float* uniform, float* logits0, void* stream);
+/* same, host buffers (pageable or pinned): H2D of tokens(+noise, +uniform), D2H of tokens inside the call */
 int gn_generate_host(gn_model* m, int32_t* tokens_host, int B, int t_prompt, int steps, float temperature,
-                     int unmask_mode, const float* noise_host, void* stream);
+                     int unmask_mode, const float* noise_host, const float* uniform_host, void* stream);
 
 /* genie/evaluate.py:82-122,173-179 + eval_utils.py:44-77: temporally teacher-forced evaluation of gt [B,T,S].
  * For t in 1..T-1: mask frames >= t, MaskGIT `steps` steps, CE of the step-0 logits against gt[:,t], token
  * accuracy of the final samples.  acc (device, 4 doubles) is ACCUMULATED into:
  *   acc[0] += sum of per-token CE, acc[1] += tokens, acc[2] += argmax-correct tokens (step-0 logits),
- *   acc[3] += sample == gt tokens.   noise [T-1, steps-1, B, S].  samples_out [B, T-1, S] nullable. */
-int gn_teacher_forced_eval(gn_model* m, const int32_t* gt, int B, int steps, int unmask_mode, const float* noise,
-                           int32_t* samples_out, double* acc, void* stream);
+ *   acc[3] += sample == gt tokens.   noise [T-1, steps-1, B, S];  uniform [T-1, steps, B, S, NV] (temperature >
+ *   1e-8 only, evaluate.py --temperature).  samples_out [B, T-1, S] nullable. */
+int gn_teacher_forced_eval(gn_model* m, const int32_t* gt, int B, int steps, float temperature, int unmask_mode,
+                           const float* noise, const float* uniform, int32_t* samples_out, double* acc, void* stream);
 
 /* STMaskGIT.forward (st_mask_git.py:267-279): masked-mean factored CE + accuracy over frames 1..T-1.
  * input_ids/labels [B,T,S]; acc (device, 4 doubles) accumulated as above over positions where
@@ -127,7 +132,9 @@ int gn_linear_forward(const void* a, const void* w, const float* bias, const flo
                       int M, int N, int K, int epi, int in_bf16, int out_bf16, int force_simt, void* stream);
 
 /* decode-step kernels exposed for isolated bit-exact tests against the oracle */
-int gn_sample_tokens(const float* logits_rows, int R, int V, int NV, int32_t* samples, float* conf, void* stream);
+/* uniform: nullptr = argmax; [R, NV] = inverse-CDF categorical draw (see gn_maskgit_generate) */
+int gn_sample_tokens(const float* logits_rows, int R, int V, int NV, const float* uniform, int32_t* samples,
+                     float* conf, void* stream);
 int gn_remask_step(int32_t* prompt_frame, int64_t clip_stride, const int32_t* samples, const float* conf_or_noise,
                    uint8_t* unmasked, int32_t* samples_out, int B, int S, int n_mask, int last_step, int mask_id,
                    void* stream);

@@ -305,18 +305,33 @@ def stable_argsort(x: torch.Tensor) -> torch.Tensor:
     return torch.sort(x, dim=1, stable=True).indices
 
 
+def categorical_icdf(probs_BVHW: torch.Tensor, u_BHW: torch.Tensor) -> torch.Tensor:
+    """One draw per position from Categorical(probs / temperature) (st_mask_git.py:184-187).  Categorical divides
+    its `probs` argument by their sum, so the temperature cancels and the distribution is `probs` itself; the draw
+    is the inverse CDF at the given uniform: min{c : cumsum(p)[c] > u * sum(p)} (last index if rounding leaves none).
+    The reference draws with torch.multinomial from the global RNG, which no other implementation can replay, so
+    parity for this branch is (a) exact for a given uniform tensor, (b) distributional against Categorical."""
+    B, V = probs_BVHW.shape[0], probs_BVHW.shape[1]
+    p = probs_BVHW.reshape(B, V, -1).to(torch.float64)
+    cdf = torch.cumsum(p, dim=1)
+    target = u_BHW.reshape(B, 1, -1).to(torch.float64) * cdf[:, -1:, :]
+    hit = cdf > target
+    first = torch.where(hit.any(dim=1), hit.to(torch.int8).argmax(dim=1), torch.full_like(hit[:, 0], V - 1, dtype=torch.int64))
+    return first.reshape(u_BHW.shape)
+
+
 def maskgit_generate(sd, cfg: OracleConfig, prompt_THW: torch.Tensor, out_t: int, maskgit_steps: int = 1,
                      temperature: float = 0.0, unmask_mode: str = "random",
-                     noise: Optional[torch.Tensor] = None, dtype=torch.float32
-                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+                     noise: Optional[torch.Tensor] = None, dtype=torch.float32,
+                     uniform: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Mutates prompt_THW[:, out_t] in place, returns (samples [B,H,W] int64, step-0 factored logits
-    [B,V,NV,H,W]).  `noise` [steps-1,B,S] replaces torch.rand_like for unmask_mode='random'.
-    Only temperature <= 1e-8 (greedy) is supported by the oracle."""
+    [B,V,NV,H,W]).  `noise` [steps-1,B,S] replaces torch.rand_like for unmask_mode='random';
+    `uniform` [steps,B,S,NV] drives the Categorical draws when temperature > 1e-8 (see categorical_icdf)."""
     assert out_t, "maskgit_generate requires out_t > 0"
     if not bool(torch.all(prompt_THW[:, out_t:] == cfg.mask_token_id)):
         raise AssertionError(f"when generating z{out_t}, frames {out_t} and later must be masked")
-    if temperature > 1e-8:
-        raise NotImplementedError("oracle implements the greedy (temperature 0) branch only")
+    if temperature > 1e-8 and uniform is None:
+        uniform = torch.rand(maskgit_steps, prompt_THW.shape[0], cfg.S, cfg.num_factored_vocabs)
     B, T, H, W = prompt_THW.shape
     S, V, NV = cfg.S, cfg.factored_vocab_size, cfg.num_factored_vocabs
     unmasked = torch.zeros(B, S, dtype=torch.bool)
@@ -332,7 +347,10 @@ def maskgit_generate(sd, cfg: OracleConfig, prompt_THW: torch.Tensor, out_t: int
         conf = torch.ones(B, H, W, dtype=probs.dtype)
         for i in reversed(range(NV)):                         # high vocab first (flip(2))
             p = probs[:, :, i]
-            s = p.argmax(dim=1)
+            if temperature <= 1e-8:
+                s = p.argmax(dim=1)
+            else:
+                s = categorical_icdf(p, uniform[step, :, :, i].reshape(B, H, W))
             samples = samples * V + s
             conf = conf * torch.gather(p, 1, s.unsqueeze(1)).squeeze(1)
         prev_unmasked = unmasked.clone()

@@ -106,7 +106,7 @@ def test_sample_tokens_bit_exact(lib):
     logits = (torch.randn(R, NV * V) * 3).cuda()
     samples = torch.empty(R, dtype=torch.int32, device="cuda")
     conf = torch.empty(R, dtype=torch.float32, device="cuda")
-    _l.check(L.gn_sample_tokens(P(logits), R, V, NV, P(samples), P(conf), None))
+    _l.check(L.gn_sample_tokens(P(logits), R, V, NV, None, P(samples), P(conf), None))
     lc = logits.cpu().reshape(R, NV, V)
     probs = torch.softmax(lc, dim=2)
     ids = torch.zeros(R, dtype=torch.int64)
@@ -126,7 +126,7 @@ def test_sample_tokens_tie_breaks_low_index(lib):
     logits[2, 512 + 9] = logits[2, 512 + 8] = 1.0  # tie in vocab 1 -> 8
     samples = torch.empty(4, dtype=torch.int32, device="cuda")
     conf = torch.empty(4, dtype=torch.float32, device="cuda")
-    _l.check(L.gn_sample_tokens(P(logits), 4, 512, 2, P(samples), P(conf), None))
+    _l.check(L.gn_sample_tokens(P(logits), 4, 512, 2, None, P(samples), P(conf), None))
     assert samples.cpu().tolist() == [0, 7, 8 * 512, 0]
 
 
@@ -206,3 +206,51 @@ def test_cross_entropy_matches_torch(lib):
         assert a[1].item() == sel.sum().item()
         assert abs(a[0].item() - ce[sel].sum().item()) < 1e-3 * R
         assert a[2].item() == ok[sel].sum().item()
+
+
+def test_sample_tokens_categorical_inverse_cdf(lib):
+    """temperature > 0 branch (st_mask_git.py:182-187): inverse-CDF draw from caller-supplied uniforms.  Ids must
+    equal the float64 inverse CDF of the same logits except where u*sum lies within fp32 rounding of a CDF step."""
+    L, _l = lib
+    torch.manual_seed(1)
+    R, V, NV = 4096, 512, 2
+    logits = (torch.randn(R, NV * V) * 4).cuda()
+    u = torch.rand(R, NV, generator=torch.Generator().manual_seed(2))
+    u[0] = 0.0
+    u[1] = 0.99999994
+    samples = torch.empty(R, dtype=torch.int32, device="cuda")
+    conf = torch.empty(R, dtype=torch.float32, device="cuda")
+    _l.check(L.gn_sample_tokens(P(logits), R, V, NV, P(u.cuda()), P(samples), P(conf), None))
+    lc = logits.cpu().reshape(R, NV, V).double()
+    probs = torch.softmax(lc, dim=2)
+    cdf = torch.cumsum(probs, dim=2)
+    got = samples.cpu().long()
+    cf = torch.ones(R, dtype=torch.float64)
+    mism = 0
+    for i in range(NV):
+        f = (got // (V ** i)) % V
+        hit = cdf[:, i] > u[:, i:i + 1].double()
+        ref = torch.where(hit.any(dim=1), hit.to(torch.int8).argmax(dim=1), torch.full((R,), V - 1))
+        bad = f != ref
+        # a mismatch is only legitimate at a CDF step: |cdf[candidate] - u| tiny for the lower of the two candidates
+        lo = torch.minimum(f, ref)
+        gap = (cdf[:, i].gather(1, lo[:, None])[:, 0] - u[:, i].double()).abs()
+        assert bool((gap[bad] < 1e-5).all())
+        assert bool(((f - ref).abs()[bad] <= 1).all())
+        mism += int(bad.sum())
+        cf = cf * probs[:, i].gather(1, f[:, None])[:, 0]
+    print("categorical boundary mismatches:", mism, "of", R * NV)
+    assert mism <= 4
+    assert torch.allclose(conf.cpu().double(), cf, rtol=2e-5, atol=0)
+    # distribution: 4096 draws from ONE row's distribution follow softmax (chi-square z-score)
+    row = (torch.randn(1, NV * V) * 3).repeat(R, 1).cuda()
+    _l.check(L.gn_sample_tokens(P(row), R, V, NV, P(u.cuda()), P(samples), P(conf), None))
+    p0 = torch.softmax(row[0].cpu().double().reshape(NV, V), dim=1)
+    f0 = (samples.cpu().long() % V)
+    counts = torch.bincount(f0[2:], minlength=V).double()
+    exp = p0[0] * (R - 2)
+    big = exp >= 5
+    chi2 = float(((counts[big] - exp[big]) ** 2 / exp[big]).sum() +
+                 (counts[~big].sum() - exp[~big].sum()) ** 2 / exp[~big].sum())
+    dof = int(big.sum())
+    assert abs(chi2 - dof) / math.sqrt(2 * dof) < 5

@@ -338,3 +338,41 @@ def test_folded_layernorm_138m():
     b = build_b200_model(kw, sd, precision="bf16", fold_ln=False).compute_logits(ids.cuda())
     print(f"138M fold vs separate LN rel {rel_fro(a, b):.3e}")
     assert rel_fro(a, b) < 1e-2
+
+
+@pytest.mark.parametrize("name", TINY)
+def test_tiny_maskgit_categorical_sampling_matches_oracle(name):
+    """temperature > 0 (st_mask_git.py:182-187) with the same uniforms on both sides: tokens identical in fp32 mode,
+    through maskgit_generate, generate and the K/V-cached path."""
+    z = load_golden(name)
+    kw, sd = golden_cfg(z), golden_sd(z)
+    cfg = O.OracleConfig(**kw)
+    B = z["prompt"].shape[0]
+    noise = torch.from_numpy(z["noise"])
+    u = torch.rand(3, B, cfg.S, cfg.num_factored_vocabs, generator=torch.Generator().manual_seed(31))
+    ref, _ = O.maskgit_generate(sd, cfg, torch.from_numpy(z["prompt"]).clone(), 2, 3, temperature=0.7, noise=noise,
+                                uniform=u)
+    greedy = torch.from_numpy(z["samples"])
+    assert not torch.equal(ref, greedy)
+    for kv in (False, True):
+        m = build_b200_model(kw, sd, precision="fp32", kv_cache=kv)
+        prompt = torch.from_numpy(z["prompt"]).cuda()
+        s, fl = m.maskgit_generate(prompt, 2, maskgit_steps=3, temperature=0.7, noise=noise, uniform=u)
+        assert torch.equal(s.cpu(), ref)
+        assert rel_fro(fl, torch.from_numpy(z["logits0"])) < TOL["fp32"]
+        # no uniform given: drawn from the device generator, still a valid sample (ids in range)
+        prompt = torch.from_numpy(z["prompt"]).cuda()
+        s2, _ = m.maskgit_generate(prompt, 2, maskgit_steps=3, temperature=1.0, noise=noise)
+        assert int(s2.min()) >= 0 and int(s2.max()) < cfg.image_vocab_size
+    ids = torch.from_numpy(z["ids"])
+    gn = torch.from_numpy(z["gen_noise"])
+    gu = torch.rand(2, 2, B, cfg.S, cfg.num_factored_vocabs, generator=torch.Generator().manual_seed(32))
+    full = ids.clone()
+    full[:, 2:] = cfg.mask_token_id
+    for i, t in enumerate((2, 3)):                 # oracle AR loop with per-frame uniforms
+        s, _ = O.maskgit_generate(sd, cfg, full, t, 2, temperature=1.0, noise=gn[i], uniform=gu[i])
+        full[:, t] = s
+    m = build_b200_model(kw, sd, precision="fp32", kv_cache=True)
+    gen = m.generate(ids[:, :2].reshape(B, -1).cuda(), None, max_new_tokens=2 * cfg.S, maskgit_steps=2,
+                     temperature=1.0, noise=gn, uniform=gu)
+    assert torch.equal(gen.cpu(), full.reshape(B, -1))

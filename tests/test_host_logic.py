@@ -65,7 +65,7 @@ def test_no_cpu_fallback_and_argument_errors():
         m.maskgit_generate(ids.clone(), 0)
     with pytest.raises(NotImplementedError, match="unmask_mode"):
         m.maskgit_generate(ids.clone(), 2, unmask_mode="nope")
-    with pytest.raises(NotImplementedError, match="temperature"):
+    with pytest.raises(pkg.GnError, match="no CPU fallback"):       # temperature > 0 is a device path too
         m.maskgit_generate(ids.clone(), 2, temperature=1.0)
     with pytest.raises(AssertionError, match="multiple of"):
         m.generate(ids[:, :2].reshape(2, -1), None, max_new_tokens=7)
