@@ -82,6 +82,30 @@ inline cudaError_t launch_kernel(int cat, void (*kern)(KArgs...), dim3 grid, dim
   return e;
 }
 
+// same, as thread-block clusters of `cluster_x` CTAs along x (grid.x must be a multiple of cluster_x)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel_cluster(int cat, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                         cudaStream_t st, int cluster_x, Args&&... args) {
+  if (g_prof_on) prof_before(cat, st);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_x;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 2 : 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  if (g_prof_on) prof_after(st);
+  return e;
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -2,11 +2,20 @@
 #include "gemm.cuh"
 #include "ptx.cuh"
 #include "tensormap.cuh"
+#include <cstdlib>
 #include <vector>
 
 namespace gn {
 
 unsigned long long g_launch_count = 0;
+
+static bool env_on(const char* name, bool dflt) {
+  const char* v = getenv(name);
+  if (!v || !*v) return dflt;
+  return !(v[0] == '0' || v[0] == 'n' || v[0] == 'N' || v[0] == 'f' || v[0] == 'F');
+}
+// GENIE_B200_PAIR=0 falls back to single-CTA 128 x 256 tiles (A/B switch for profiling)
+static bool g_use_pair = env_on("GENIE_B200_PAIR", true);
 
 double g_gemm_flops_issued = 0.0;
 
@@ -32,12 +41,16 @@ constexpr int RES_BUFS = 4;      // residual epilogue: in-place staging buffers 
                                  // emit the bf16 copy, so that a 3-stage operand ring still fits)
 constexpr int res_bufs(int block_n, bool dual) { return (block_n > 128 && dual) ? 3 : RES_BUFS; }
 
-template <int BLOCK_N, int EPI, typename OutT, bool DUAL>
+// CTAS = 2: CTA-pair tiles (tcgen05 cta_group::2).  One tile is 256 rows x BLOCK_N columns; each CTA of the pair stages
+// its own 128 rows of A and ONE HALF of the B tile, so a k-block costs A + B/2 bytes of L2->SM traffic per SM instead
+// of A + B: the linear layers of this model (K = 512 / 2048) are bound by the chip-wide L2->SM throughput
+// (~6.2 KB per L2 clock, profiles/), not by the tensor pipe.
+template <int BLOCK_N, int EPI, typename OutT, bool DUAL, int CTAS = 1>
 struct GemmSmem {
   static constexpr int NUM_EPI_WARPS = EpiCfg<EPI>::WARPS;
   static constexpr int COLS_PER_WARP = BLOCK_N / (NUM_EPI_WARPS / 4);   // columns of the tile one warp handles
   static constexpr int OUT_BUFS = EPI == EPI_RESID ? res_bufs(BLOCK_N, DUAL) : (NUM_EPI_WARPS == 8 ? 1 : 2);
-  static constexpr int B_TILE_BYTES = BLOCK_N * TILE_K_BYTES;
+  static constexpr int B_TILE_BYTES = (BLOCK_N / CTAS) * TILE_K_BYTES;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int OUT_STAGE_BYTES = 32 * EPI_COLS * (int)sizeof(OutT);          // per warp per buffer
   static constexpr int OUT2_STAGE_BYTES = DUAL ? 32 * EPI_COLS * 2 : 0;
@@ -97,19 +110,23 @@ __device__ __forceinline__ void stage_row_chunk<bf16>(uint8_t* buf, uint32_t lan
   }
 }
 
-template <typename InT, int BLOCK_N, int EPI, typename OutT, bool DUAL>
+template <typename InT, int BLOCK_N, int EPI, typename OutT, bool DUAL, int CTAS>
 __global__ void __launch_bounds__(32 * (2 + EpiCfg<EPI>::WARPS), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
                     const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const TcArgs args) {
-  using SM = GemmSmem<BLOCK_N, EPI, OutT, DUAL>;
+  using SM = GemmSmem<BLOCK_N, EPI, OutT, DUAL, CTAS>;
   constexpr int NUM_EPI_WARPS = SM::NUM_EPI_WARPS;
   constexpr int STAGES = SM::STAGES;
   constexpr int BLOCK_K = TILE_K_BYTES / (int)sizeof(InT);     // 64 (bf16) or 32 (tf32)
   constexpr int TMEM_COLS = NUM_ACC_STAGES * BLOCK_N;          // 128 / 256 / 512
   constexpr uint32_t IDESC =
-      umma_idesc(sizeof(InT) == 2 ? UMMA_FMT_BF16 : UMMA_FMT_TF32, BLOCK_M, BLOCK_N);
+      umma_idesc(sizeof(InT) == 2 ? UMMA_FMT_BF16 : UMMA_FMT_TF32, BLOCK_M * CTAS, BLOCK_N);
+  // CTA pair: rank within the pair, pair index, number of pairs (CTAS == 1: rank 0, one "pair" per CTA)
+  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const int pair = (int)blockIdx.x / CTAS;
+  const int num_pairs = (int)gridDim.x / CTAS;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -128,7 +145,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
 
-  const int num_m = (args.M + BLOCK_M - 1) / BLOCK_M;
+  const int num_m = (args.M + BLOCK_M * CTAS - 1) / (BLOCK_M * CTAS);
   const int num_n = args.N / BLOCK_N;
   const int num_tiles = num_m * num_n;
   const int num_kb = args.cin_blocks > 0 ? 9 * args.cin_blocks : (args.K + BLOCK_K - 1) / BLOCK_K;
@@ -145,14 +162,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < NUM_ACC_STAGES; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], NUM_EPI_WARPS);
+      mbar_init(&acc_empty[s], NUM_EPI_WARPS * CTAS);   // the leader's barrier collects both CTAs' epilogue warps
     }
     for (int s = 0; s < NUM_EPI_WARPS * RES_BUFS; ++s) mbar_init(&res_bar[s], 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if (CTAS == 2) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
+    else tmem_alloc<TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();    // the peer's barriers are initialised before anything arrives on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched only below
@@ -162,32 +183,43 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int m_blk = tile / num_n, n_blk = tile % num_n;
+        const int m_row0 = (m_blk * CTAS + (int)cta_rank) * BLOCK_M;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
-          if (args.cin_blocks > 0) {
-            // conv: tile = th x tw output pixels of image n starting at (y0, x0); k-block = (tap, channel block)
-            const int P = args.Ho * args.Wo;
-            const int p0 = m_blk * BLOCK_M;
-            const int n = p0 / P, rem = p0 % P;
-            const int y0 = rem / args.Wo, x0 = rem % args.Wo;
-            const int tap = kb / args.cin_blocks, cib = kb % args.cin_blocks;
-            tma_load_4d(smem_a + stage * A_TILE_BYTES, &tmA, &full_bar[stage], cib * BLOCK_K,
-                        x0 * args.stride + tap % 3 - 1, y0 * args.stride + tap / 3 - 1, n);
-          } else
-          tma_load_2d(smem_a + stage * A_TILE_BYTES, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-          tma_load_2d(smem_b + stage * SM::B_TILE_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          if constexpr (CTAS == 2) {
+            // both CTAs' bytes complete on the LEADER's barrier (which the MMA issuer waits on)
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * SM::STAGE_BYTES);
+            const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_pair(smem_a + stage * A_TILE_BYTES, &tmA, bar, kb * BLOCK_K, m_row0);
+            tma_load_2d_pair(smem_b + stage * SM::B_TILE_BYTES, &tmB, bar, kb * BLOCK_K,
+                             n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / 2));
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
+            if (args.cin_blocks > 0) {
+              // conv: tile = th x tw output pixels of image n starting at (y0, x0); k-block = (tap, channel block)
+              const int P = args.Ho * args.Wo;
+              const int p0 = m_blk * BLOCK_M;
+              const int n = p0 / P, rem = p0 % P;
+              const int y0 = rem / args.Wo, x0 = rem % args.Wo;
+              const int tap = kb / args.cin_blocks, cib = kb % args.cin_blocks;
+              tma_load_4d(smem_a + stage * A_TILE_BYTES, &tmA, &full_bar[stage], cib * BLOCK_K,
+                          x0 * args.stride + tap % 3 - 1, y0 * args.stride + tap / 3 - 1, n);
+            } else {
+              tma_load_2d(smem_a + stage * A_TILE_BYTES, &tmA, &full_bar[stage], kb * BLOCK_K, m_row0);
+            }
+            tma_load_2d(smem_b + stage * SM::B_TILE_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA only)
+    if (lane == 0 && cta_rank == 0) {
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         mbar_wait(&acc_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
@@ -199,15 +231,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int k = 0; k < TILE_K_BYTES / 32; ++k) {
             // advance 32 B (= one UMMA_K slice) inside the swizzle atom: +2 in 16-byte units
-            if (sizeof(InT) == 2)
-              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
-            else
-              umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+            if constexpr (CTAS == 2) {
+              if (sizeof(InT) == 2)
+                umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+              else
+                umma_tf32_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+            } else {
+              if (sizeof(InT) == 2)
+                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+              else
+                umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+            }
           }
-          umma_commit(&empty_bar[stage]);          // smem slot reusable once these MMAs retire
+          // smem slot reusable (in both CTAs) once these MMAs retire
+          if constexpr (CTAS == 2) umma_commit_pair(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&acc_full[as]);                // accumulator complete
+        // accumulator complete (each CTA's epilogue reads its own 128 rows from its own TMEM)
+        if constexpr (CTAS == 2) umma_commit_pair(&acc_full[as]);
+        else umma_commit(&acc_full[as]);
         if (++as == NUM_ACC_STAGES) { as = 0; aphase ^= 1; }
       }
     }
@@ -225,6 +268,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     float* scsum = bias_smem + (NUM_EPI_WARPS + ew) * SM::COLS_PER_WARP;
     const bool has_bias = args.bias != nullptr;
     const bool has_ln = args.ln_stats != nullptr;
+    // hand an accumulator stage back to the (leader's) MMA issuer
+    auto release_acc = [&](uint32_t stage_idx) {
+      if (CTAS == 2 && cta_rank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[stage_idx]), 0));
+      else mbar_arrive(&acc_empty[stage_idx]);
+    };
     float ln_r = 1.f, ln_t = 0.f;   // per-row rstd and -rstd*mean of the folded LayerNorm
     // stage this tile's bias slice in shared memory (per warp) BEFORE waiting for the accumulator, so the
     // global-load latency hides behind the MMA of the tile
@@ -283,23 +331,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       constexpr int RB = SM::OUT_BUFS;   // staging buffers per warp
       constexpr int RP = RB - 2;         // residual chunks requested ahead of use
       uint64_t* rbar = res_bar + ew * RES_BUFS;
-      const int my_tiles = (int)blockIdx.x < num_tiles ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+      const int my_tiles = pair < num_tiles ? (num_tiles - pair + num_pairs - 1) / num_pairs : 0;
       const int total_chunks = my_tiles * CH;
       auto issue_residual = [&](int g) {           // lane 0 only
-        const int t = blockIdx.x + (g / CH) * gridDim.x;
+        const int t = pair + (g / CH) * num_pairs;
         const int mb = t / num_n, nb = t % num_n;
         const int b = g % RB;
         mbar_arrive_expect_tx(&rbar[b], SM::OUT_STAGE_BYTES);
         tma_load_2d(st0 + b * SM::OUT_STAGE_BYTES, &tmRes, &rbar[b], nb * BLOCK_N + (g % CH) * EPI_COLS,
-                    mb * BLOCK_M + q * 32);
+                    (mb * CTAS + (int)cta_rank) * BLOCK_M + q * 32);
       };
       if (lane == 0) {
         for (int g0 = 0; g0 < RP && g0 < total_chunks; ++g0) issue_residual(g0);
       }
       int g = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int m_blk = tile / num_n, n_blk = tile % num_n;
-        const int row0 = m_blk * BLOCK_M + q * 32;
+        const int row0 = (m_blk * CTAS + (int)cta_rank) * BLOCK_M + q * 32;
         stage_bias(n_blk);
         mbar_wait(&acc_full[as], aphase);
         tc_fence_after();
@@ -318,7 +366,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (c == CH - 1) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[as]);
+            if (lane == 0) release_acc(as);
           }
           float v[EPI_COLS];
 #pragma unroll
@@ -355,9 +403,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     } else {
       uint32_t buf = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int m_blk = tile / num_n, n_blk = tile % num_n;
-        const int row0 = m_blk * BLOCK_M + q * 32;
+        const int row0 = (m_blk * CTAS + (int)cta_rank) * BLOCK_M + q * 32;
         stage_bias(n_blk);
         load_row_stats(row0 + (int)lane);
         mbar_wait(&acc_full[as], aphase);
@@ -382,7 +430,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // accumulator stage fully read into registers: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[as]);
+            if (lane == 0) release_acc(as);
           }
           float v[EPI_COLS];
 #pragma unroll
@@ -432,16 +480,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();    // neither CTA may retire while the pair's MMAs / commits still target it
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (CTAS == 2) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+    else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
-template <typename InT, int BLOCK_N, int EPI, typename OutT, bool DUAL>
+template <typename InT, int BLOCK_N, int EPI, typename OutT, bool DUAL, int CTAS = 1>
 int launch_tc(const LinearArgs& a, cudaStream_t stream) {
-  using SM = GemmSmem<BLOCK_N, EPI, OutT, DUAL>;
+  using SM = GemmSmem<BLOCK_N, EPI, OutT, DUAL, CTAS>;
   constexpr int BLOCK_K = TILE_K_BYTES / (int)sizeof(InT);
   const CUtensorMapDataType in_dt = sizeof(InT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   const CUtensorMapDataType out_dt =
@@ -457,7 +507,7 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
   } else
   GN_PROPAGATE(make_tensor_map_2d(&tmA, a.A, in_dt, sizeof(InT), a.K, a.M, a.lda, BLOCK_K, BLOCK_M,
                                   CU_TENSOR_MAP_SWIZZLE_128B));
-  GN_PROPAGATE(make_tensor_map_2d(&tmB, a.W, in_dt, sizeof(InT), a.K, a.N, a.ldw, BLOCK_K, BLOCK_N,
+  GN_PROPAGATE(make_tensor_map_2d(&tmB, a.W, in_dt, sizeof(InT), a.K, a.N, a.ldw, BLOCK_K, BLOCK_N / CTAS,
                                   CU_TENSOR_MAP_SWIZZLE_128B));
   GN_PROPAGATE(make_tensor_map_2d(&tmO, a.out, out_dt, sizeof(OutT), a.N, a.M, a.ldo, EPI_COLS, 32,
                                   sizeof(OutT) == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B));
@@ -488,19 +538,43 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
     tmK = tmO;
     tmV = tmO;
   }
-  auto kern = gemm_tcgen05_kernel<InT, BLOCK_N, EPI, OutT, DUAL>;
+  auto kern = gemm_tcgen05_kernel<InT, BLOCK_N, EPI, OutT, DUAL, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
     GN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     attr_set = true;
   }
-  const int num_tiles = ceil_div(a.M, BLOCK_M) * (a.N / BLOCK_N);
+  const int num_tiles = ceil_div(a.M, BLOCK_M * CTAS) * (a.N / BLOCK_N);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   static int cached_sms = 0;
   if (!cached_sms) cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev);
   sms = cached_sms > 0 ? cached_sms : 148;
-  const int grid = num_tiles < sms ? num_tiles : sms;
+  int grid = num_tiles < sms ? num_tiles : sms;
+  if (CTAS == 2) {
+    // persistent pairs: as many 2-CTA clusters as can be co-resident (one CTA per SM, both SMs of a TPC)
+    static int max_pairs = 0;
+    if (!max_pairs) {
+      cudaLaunchConfig_t qc{};
+      qc.gridDim = dim3(sms);
+      qc.blockDim = dim3(32 * (2 + SM::NUM_EPI_WARPS));
+      qc.dynamicSmemBytes = SM::TOTAL;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa;
+      qc.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &qc) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = sms / 2;
+      }
+      max_pairs = n < sms / 2 ? n : sms / 2;
+    }
+    grid = 2 * (num_tiles < max_pairs ? num_tiles : max_pairs);
+  }
   TcArgs t{a.M, a.N, a.K, a.bias, a.resid, a.ldr, a.round_out_tf32, 0, 0, 0, 0, 0, 1, nullptr, 0, 0, nullptr, nullptr,
            0, 0, 0, 0, 0};
   if (kv) { t.kv_d = a.kv_d; t.kv_hd = a.kv_hd; t.kv_S = a.kv_S; t.kv_Tact = a.kv_Tact; t.kv_t0 = a.kv_t0; }
@@ -511,20 +585,25 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
   t.ln_stats = a.ln_stats; t.ln_np = a.ln_np; t.ln_d = a.ln_d; t.ln_colsum = a.ln_colsum; t.stats_out = a.stats_out;
   g_gemm_flops_issued += 2.0 * a.M * (double)a.N * a.K;
   const int cat = EPI == EPI_RESID ? PC_GEMM_RESID : (EPI == EPI_GELU ? PC_GEMM_GELU : PC_GEMM_STORE);
-  GN_CUDA_CHECK(launch_kernel(cat, kern, dim3(grid), dim3(32 * (2 + SM::NUM_EPI_WARPS)), SM::TOTAL, stream, tmA, tmB, tmO, tmO2, tmR, tmK, tmV, t));
+  if (CTAS == 2)
+    GN_CUDA_CHECK(launch_kernel_cluster(cat, kern, dim3(grid), dim3(32 * (2 + SM::NUM_EPI_WARPS)), SM::TOTAL, stream, 2,
+                                        tmA, tmB, tmO, tmO2, tmR, tmK, tmV, t));
+  else
+    GN_CUDA_CHECK(launch_kernel(cat, kern, dim3(grid), dim3(32 * (2 + SM::NUM_EPI_WARPS)), SM::TOTAL, stream, tmA, tmB,
+                                tmO, tmO2, tmR, tmK, tmV, t));
   ++g_launch_count;
   return GN_OK;
 }
 
-template <typename InT, int BLOCK_N>
+template <typename InT, int BLOCK_N, int CTAS = 1>
 int dispatch_epi(const LinearArgs& a, cudaStream_t s) {
   if (a.epi == EPI_STORE) {
-    return a.out_bf16 ? launch_tc<InT, BLOCK_N, EPI_STORE, bf16, false>(a, s)
-                      : launch_tc<InT, BLOCK_N, EPI_STORE, float, false>(a, s);
+    return a.out_bf16 ? launch_tc<InT, BLOCK_N, EPI_STORE, bf16, false, CTAS>(a, s)
+                      : launch_tc<InT, BLOCK_N, EPI_STORE, float, false, CTAS>(a, s);
   }
   if (a.epi == EPI_GELU) {
-    return a.out_bf16 ? launch_tc<InT, BLOCK_N, EPI_GELU, bf16, false>(a, s)
-                      : launch_tc<InT, BLOCK_N, EPI_GELU, float, false>(a, s);
+    return a.out_bf16 ? launch_tc<InT, BLOCK_N, EPI_GELU, bf16, false, CTAS>(a, s)
+                      : launch_tc<InT, BLOCK_N, EPI_GELU, float, false, CTAS>(a, s);
   }
   if (a.epi == EPI_RESID) {
     if (a.out_bf16) { set_error("EPI_RESID writes the fp32 residual stream"); return GN_ERR_INVALID; }
@@ -532,8 +611,8 @@ int dispatch_epi(const LinearArgs& a, cudaStream_t s) {
       return a.out2 ? launch_tc<InT, BLOCK_N, EPI_RESID, float, true>(a, s)
                     : launch_tc<InT, BLOCK_N, EPI_RESID, float, false>(a, s);
     } else {   // 256-wide: 3 residual staging buffers when the bf16 copy is emitted too
-      return a.out2 ? launch_tc<InT, BLOCK_N, EPI_RESID, float, true>(a, s)
-                    : launch_tc<InT, BLOCK_N, EPI_RESID, float, false>(a, s);
+      return a.out2 ? launch_tc<InT, BLOCK_N, EPI_RESID, float, true, CTAS>(a, s)
+                    : launch_tc<InT, BLOCK_N, EPI_RESID, float, false, CTAS>(a, s);
     }
   }
   set_error("unknown epilogue %d", a.epi);
@@ -546,7 +625,11 @@ int dispatch_n(const LinearArgs& a, cudaStream_t s) {
   // Residual epilogues stage 4 fp32 buffers per warp, so they normally take BLOCK_N = 128 to keep a deep TMA ring;
   // for long-K residual GEMMs (fc2: K = 4d) the 128-wide tile is operand-bandwidth bound (A+B = 128 B/clk of smem
   // reads per MMA cycle), so those use 256 with a 3-stage ring.
-  if (a.N % 256 == 0 && (a.epi != EPI_RESID || a.K >= 1024)) return dispatch_epi<InT, 256>(a, s);
+  // 256-wide tiles run as CTA pairs (256 x 256 per pair, cta_group::2) unless disabled or a convolution
+  if (a.N % 256 == 0 && (a.epi != EPI_RESID || a.K >= 1024)) {
+    if (g_use_pair && !a.conv && a.M > BLOCK_M) return dispatch_epi<InT, 256, 2>(a, s);
+    return dispatch_epi<InT, 256>(a, s);
+  }
   if (a.N % 128 == 0) return dispatch_epi<InT, 128>(a, s);
   return dispatch_epi<InT, 64>(a, s);
 }
