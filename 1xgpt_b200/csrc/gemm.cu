@@ -49,7 +49,12 @@ template <int BLOCK_N, int EPI, typename OutT, bool DUAL, int CTAS = 1>
 struct GemmSmem {
   static constexpr int NUM_EPI_WARPS = EpiCfg<EPI>::WARPS;
   static constexpr int COLS_PER_WARP = BLOCK_N / (NUM_EPI_WARPS / 4);   // columns of the tile one warp handles
-  static constexpr int OUT_BUFS = EPI == EPI_RESID ? res_bufs(BLOCK_N, DUAL) : (NUM_EPI_WARPS == 8 ? 1 : 2);
+  // store / GELU epilogues: one staging buffer per 32-column chunk of the warp's slice (8 KB per warp), so a buffer is
+  // rewritten a whole tile after its TMA store was issued and the store's read latency never stalls the warp
+  static constexpr int EPI_BUF_BYTES = 32 * EPI_COLS * (int)sizeof(OutT);
+  static constexpr int STORE_BUFS = (COLS_PER_WARP / EPI_COLS) * EPI_BUF_BYTES <= 8192
+                                        ? COLS_PER_WARP / EPI_COLS : 8192 / EPI_BUF_BYTES;
+  static constexpr int OUT_BUFS = EPI == EPI_RESID ? res_bufs(BLOCK_N, DUAL) : STORE_BUFS;
   static constexpr int B_TILE_BYTES = (BLOCK_N / CTAS) * TILE_K_BYTES;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int OUT_STAGE_BYTES = 32 * EPI_COLS * (int)sizeof(OutT);          // per warp per buffer
@@ -80,6 +85,9 @@ struct TcArgs {
   float* stats_out;
   // K/V columns of the temporal QKV projection go to the caches (kv_d == 0: off)
   int kv_d, kv_hd, kv_S, kv_Tact, kv_t0;
+  // profiling aid (GENIE_B200_GEMM_DEBUG; results are garbage): bit 0 = store/GELU epilogues release the accumulator
+  // without reading or storing it, bit 1 = the producer signals the stages without loading them
+  int dbg;
 };
 
 template <typename OutT>
@@ -188,6 +196,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int m_row0 = (m_blk * CTAS + (int)cta_rank) * BLOCK_M;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (args.dbg & 2) {
+            if (cta_rank == 0) mbar_arrive(&full_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if constexpr (CTAS == 2) {
             // both CTAs' bytes complete on the LEADER's barrier (which the MMA issuer waits on)
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * SM::STAGE_BYTES);
@@ -410,6 +423,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         load_row_stats(row0 + (int)lane);
         mbar_wait(&acc_full[as], aphase);
         tc_fence_after();
+        if (args.dbg & 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) release_acc(as);
+          if (++as == NUM_ACC_STAGES) { as = 0; aphase ^= 1; }
+          continue;
+        }
         const uint32_t acc_addr = tmem_base + ((q * 32u) << 16) + as * BLOCK_N + col_base;
         // K/V-cache destination of this warp's 32 rows (rows are (clip, local frame, s); 32 | S)
         int kv_frame = 0, kv_pos = 0;
@@ -452,10 +472,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           // the staging buffer about to be written was last stored from OUT_BUFS steps ago
           if (lane == 0) tma_store_wait_read<SM::OUT_BUFS - 1>();
           __syncwarp();
-          stage_row_chunk<OutT>(st0 + buf * SM::OUT_STAGE_BYTES, lane, v);
+          if (!(args.dbg & 8)) stage_row_chunk<OutT>(st0 + buf * SM::OUT_STAGE_BYTES, lane, v);
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && !(args.dbg & 4)) {
             if (EPI == EPI_STORE && sizeof(OutT) == 2 && args.kv_d > 0 && col0 >= args.kv_d) {
               const int part = col0 >= 2 * args.kv_d ? 2 : 1;
               const int cc = col0 - part * args.kv_d;
@@ -466,7 +486,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             tma_store_commit();
           }
-          if (SM::OUT_BUFS > 1) buf ^= 1;
+          if (SM::OUT_BUFS > 1) buf = (buf + 1 == SM::OUT_BUFS) ? 0 : buf + 1;
         };
 #pragma unroll 1
         for (int c2 = 0; c2 < CH; c2 += 2) {
@@ -576,7 +596,11 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
     grid = 2 * (num_tiles < max_pairs ? num_tiles : max_pairs);
   }
   TcArgs t{a.M, a.N, a.K, a.bias, a.resid, a.ldr, a.round_out_tf32, 0, 0, 0, 0, 0, 1, nullptr, 0, 0, nullptr, nullptr,
-           0, 0, 0, 0, 0};
+           0, 0, 0, 0, 0, 0};
+  {
+    const char* e = getenv("GENIE_B200_GEMM_DEBUG");   // re-read per launch: scripts/gemm_ablation.py flips it
+    t.dbg = e ? atoi(e) : 0;
+  }
   if (kv) { t.kv_d = a.kv_d; t.kv_hd = a.kv_hd; t.kv_S = a.kv_S; t.kv_Tact = a.kv_Tact; t.kv_t0 = a.kv_t0; }
   if (a.conv) {
     t.cin_blocks = a.conv->Cin / BLOCK_K;
@@ -626,10 +650,10 @@ int dispatch_n(const LinearArgs& a, cudaStream_t s) {
   // for long-K residual GEMMs (fc2: K = 4d) the 128-wide tile is operand-bandwidth bound (A+B = 128 B/clk of smem
   // reads per MMA cycle), so those use 256 with a 3-stage ring.
   // 256-wide tiles run as CTA pairs (256 x 256 per pair, cta_group::2) unless disabled or a convolution
-  if (a.N % 256 == 0 && (a.epi != EPI_RESID || a.K >= 1024)) {
-    if (g_use_pair && !a.conv && a.M > BLOCK_M) return dispatch_epi<InT, 256, 2>(a, s);
-    return dispatch_epi<InT, 256>(a, s);
-  }
+  const bool pair = env_on("GENIE_B200_PAIR", g_use_pair) && !a.conv && a.M > BLOCK_M;
+  if (a.N % 256 == 0 && pair && (a.epi != EPI_RESID || a.K >= 1024 || env_on("GENIE_B200_PAIR_PROJ", false)))
+    return dispatch_epi<InT, 256, 2>(a, s);
+  if (a.N % 256 == 0 && (a.epi != EPI_RESID || a.K >= 1024)) return dispatch_epi<InT, 256>(a, s);
   if (a.N % 128 == 0) return dispatch_epi<InT, 128>(a, s);
   return dispatch_epi<InT, 64>(a, s);
 }
@@ -701,6 +725,7 @@ int launch_simt(const LinearArgs& a, cudaStream_t s) {
 }  // namespace
 
 int resid_block_n(int N, int K, bool dual) {
+  if (N % 256 == 0 && env_on("GENIE_B200_PAIR", g_use_pair) && env_on("GENIE_B200_PAIR_PROJ", false)) return 256;
   if (N % 256 == 0 && K >= 1024) return 256;
   if (N % 128 == 0) return 128;
   return 64;
