@@ -25,6 +25,7 @@ class gn_config(C.Structure):
         ("proj_bias", C.c_int32), ("qk_norm", C.c_int32), ("mlp_bias", C.c_int32), ("mlp_ratio", C.c_float),
         ("precision", C.c_int32), ("chunk_tokens", C.c_int32), ("kv_cache", C.c_int32),
         ("generic_attention", C.c_int32), ("fold_ln", C.c_int32), ("cuda_graphs", C.c_int32),
+        ("lanes", C.c_int32),
     ]
 
 
@@ -53,6 +54,7 @@ SIGNATURES = {
     "gn_teacher_forced_eval": (_i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "gn_forward_loss": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "gn_linear_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "gn_spatial_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     "gn_sample_tokens": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "gn_remask_step": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "gn_cross_entropy": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),

@@ -713,6 +713,7 @@ int launch_temporal_attention_v2(const AttnArgs& a, int nb, int S, int T, int t0
 }
 
 int launch_spatial_attention(const AttnArgs& a, int n_frames, int S, int force_generic, cudaStream_t st) {
+  if (!force_generic && tc_spatial_supported(a, S)) return tc_spatial_attention(a, n_frames, S, st);
   if (!force_generic && fast_spatial_supported(a, S)) return fast_spatial_attention(a, n_frames, S, st);
   return launch_generic_attention(a, n_frames, S, 0, st);
 }

@@ -36,6 +36,12 @@ struct AttnArgs {
 };
 // spatial: sequences = frames; tokens of a sequence are S consecutive rows.  non-causal.
 int launch_spatial_attention(const AttnArgs& a, int n_frames, int S, int force_generic, cudaStream_t st);
+// mma.sync spatial kernel (attention_fast.cu): bf16, head_dim 64 / 32, S in {128, 256}, optional qk-LayerNorm
+bool fast_spatial_supported(const AttnArgs& a, int S);
+int fast_spatial_attention(const AttnArgs& a, int n_frames, int S, cudaStream_t st);
+// tcgen05 spatial attention (attention_tc.cu): bf16, head_dim 64, S in {128, 256}, no qk-LayerNorm
+bool tc_spatial_supported(const AttnArgs& a, int S);
+int tc_spatial_attention(const AttnArgs& a, int n_frames, int S, cudaStream_t st);
 // temporal: sequences = (clip, spatial position); token (b, tl, s) is row (b*Tq + tl)*S + s of qkv (fresh
 // frames t0..t0+Tq-1).  Keys/values of frames < t0 come from kcache/vcache [B, S, T, d] (nullptr when t0 == 0);
 // fresh k/v are written back to the caches when they are non-null.  causal.

@@ -54,7 +54,7 @@ struct gn_model {
   std::set<std::string> have;
   std::vector<void*> owned;
 
-  // chunk workspace
+  // chunk workspace of the ACTIVE lane (select_lane swaps these with lane_ws[])
   int64_t ws_tokens = 0;
   float* x = nullptr;     // [n, d] fp32 residual stream
   void* a = nullptr;      // [n, d] act
@@ -64,6 +64,22 @@ struct gn_model {
   int tv2 = 0;            // temporal attention v2: head-major K/V caches written by the temporal QKV GEMM epilogue
   void* scr_k = nullptr;  // [chunk clips * S][H][T][hd] scratch K/V for tv2 when the persistent cache is off
   void* scr_v = nullptr;
+  // Lanes: clips are independent, so the chunks of one MaskGIT step are dealt round-robin to `lanes` streams
+  // (lane 0 = the caller's stream, the others library-owned), each with its own workspace.  The GPU then has two
+  // independent kernel chains to schedule: the tail wave of one lane's persistent GEMM is filled by the other lane's
+  // next kernel and HBM-bound kernels (temporal attention, LayerNorm, proj+residual) overlap tensor-bound ones.
+  struct LaneWs {
+    int64_t ws_tokens = 0;
+    float* x = nullptr; void* a = nullptr; void* big = nullptr; void* o = nullptr; float* stats = nullptr;
+    void* scr_k = nullptr; void* scr_v = nullptr;
+  };
+  static constexpr int kMaxLanes = 4;
+  LaneWs lane_ws[kMaxLanes];
+  int lane = 0;                               // active lane
+  int lanes = 1;
+  cudaStream_t lane_stream[kMaxLanes] = {};   // [0] unused (caller's stream)
+  cudaEvent_t lane_fork = nullptr;
+  cudaEvent_t lane_join[kMaxLanes] = {};
   int fold = 0;           // folded-LayerNorm path active (bf16, qk_norm = 0, cfg.fold_ln)
   bool fold_dirty = true;
   int64_t rows_cap = 0;
@@ -116,6 +132,31 @@ void dev_free(gn_model* m, void* p) {
 void drop_graphs(gn_model* m) {
   for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second.exec);
   m->graphs.clear();
+}
+
+// make lane `i`'s workspace the active one (host enqueue is sequential, so swapping the pointers is enough)
+void select_lane(gn_model* m, int i) {
+  if (i == m->lane) return;
+  gn_model::LaneWs& cur = m->lane_ws[m->lane];
+  cur.ws_tokens = m->ws_tokens; cur.x = m->x; cur.a = m->a; cur.big = m->big; cur.o = m->o; cur.stats = m->stats;
+  cur.scr_k = m->scr_k; cur.scr_v = m->scr_v;
+  const gn_model::LaneWs& nx = m->lane_ws[i];
+  m->ws_tokens = nx.ws_tokens; m->x = nx.x; m->a = nx.a; m->big = nx.big; m->o = nx.o; m->stats = nx.stats;
+  m->scr_k = nx.scr_k; m->scr_v = nx.scr_v;
+  m->lane = i;
+}
+
+// lanes usable for a call on stream `st`: side streams are created on first use
+int lanes_for(gn_model* m, cudaStream_t st) {
+  if (m->lanes <= 1 || st == nullptr || st == cudaStreamLegacy || g_prof_on) return 1;
+  if (!m->lane_fork) {
+    GN_CUDA_CHECK(cudaEventCreateWithFlags(&m->lane_fork, cudaEventDisableTiming));
+    for (int i = 1; i < m->lanes; ++i) {
+      GN_CUDA_CHECK(cudaStreamCreateWithFlags(&m->lane_stream[i], cudaStreamNonBlocking));
+      GN_CUDA_CHECK(cudaEventCreateWithFlags(&m->lane_join[i], cudaEventDisableTiming));
+    }
+  }
+  return m->lanes;
 }
 
 int ensure_workspace(gn_model* m, int64_t n) {
@@ -369,7 +410,7 @@ int run_layers(gn_model* m, int b0, int nb, int t0, int Tact, bool use_cache, cu
 int run_layers_graphed(gn_model* m, int b0, int nb, int t0, int Tact, bool use_cache, cudaStream_t st) {
   if (!m->cfg.cuda_graphs || st == nullptr || st == cudaStreamLegacy || g_prof_on || (m->fold && m->fold_dirty))
     return run_layers(m, b0, nb, t0, Tact, use_cache, st);
-  const std::vector<int> key = {b0, nb, t0, Tact, use_cache ? 1 : 0};
+  const std::vector<int> key = {b0, nb, t0, Tact, use_cache ? 1 : 0, m->lane};
   auto it = m->graphs.find(key);
   if (it == m->graphs.end()) {
     const double f0 = m->flops_executed;
@@ -476,12 +517,32 @@ int maskgit_impl(gn_model* m, int32_t* prompt, int B, int out_t, int steps, int 
       t0 = step == 0 ? recompute_from : out_t;
       Tact = out_t + 1 - t0;
     }
-    const int cc = chunk_clips_for(m, Tact);
-    for (int b0 = 0; b0 < B; b0 += cc) {
-      const int nb = std::min(cc, B - b0);
-      GN_PROPAGATE(forward_chunk(m, prompt, b0, nb, t0, Tact, cache, st));
-      GN_PROPAGATE(readout(m, nb, Tact, out_t - t0, m->logits_frame + (int64_t)b0 * S * m->C, st));
+    const int nl = lanes_for(m, st);
+    if (nl < 0) return nl;
+    const int cc = std::max(1, std::min(chunk_clips_for(m, Tact), (B + nl - 1) / nl));
+    const int n_chunks = (B + cc - 1) / cc;
+    const int used = std::min(nl, n_chunks);
+    if (used > 1) {   // fork: the side lanes start after everything already enqueued on the caller's stream
+      GN_CUDA_CHECK(cudaEventRecord(m->lane_fork, st));
+      for (int i = 1; i < used; ++i) GN_CUDA_CHECK(cudaStreamWaitEvent(m->lane_stream[i], m->lane_fork, 0));
     }
+    int rc = GN_OK;
+    for (int b0 = 0, ci = 0; b0 < B && rc == GN_OK; b0 += cc, ++ci) {
+      const int nb = std::min(cc, B - b0);
+      const int li = ci % used;
+      cudaStream_t ls = li == 0 ? st : m->lane_stream[li];
+      select_lane(m, li);
+      rc = forward_chunk(m, prompt, b0, nb, t0, Tact, cache, ls);
+      if (rc == GN_OK) rc = readout(m, nb, Tact, out_t - t0, m->logits_frame + (int64_t)b0 * S * m->C, ls);
+    }
+    select_lane(m, 0);
+    if (used > 1) {   // join (also on the error path: the caller's stream must not run ahead of the side lanes)
+      for (int i = 1; i < used; ++i) {
+        GN_CUDA_CHECK(cudaEventRecord(m->lane_join[i], m->lane_stream[i]));
+        GN_CUDA_CHECK(cudaStreamWaitEvent(st, m->lane_join[i], 0));
+      }
+    }
+    GN_PROPAGATE(rc);
     if (step == 0) {
       if (logits0) GN_PROPAGATE(launch_logits_transpose(m->logits_frame, logits0, B, 1, S, m->C, logits0_Tout,
                                                         logits0_slot, st));
@@ -589,6 +650,7 @@ int gn_model_create(gn_model** out, const gn_config* cfg, int device) {
     probe.act_bf16 = m->act_bf16; probe.n_heads = cfg->num_heads; probe.head_dim = cfg->d_model / cfg->num_heads;
     m->tv2 = (on && !cfg->qk_norm && !cfg->generic_attention && temporal_v2_supported(probe, cfg->S, cfg->T)) ? 1 : 0;
   }
+  m->lanes = cfg->lanes <= 0 ? 2 : std::min<int>(cfg->lanes, gn_model::kMaxLanes);
   m->hid = (int)(cfg->d_model * cfg->mlp_ratio);
   m->C = cfg->num_factored_vocabs * cfg->factored_vocab_size;
   m->layers.resize(cfg->num_layers);
@@ -600,6 +662,11 @@ void gn_model_destroy(gn_model* m) {
   if (!m) return;
   DeviceGuard g(m->device);
   drop_graphs(m);
+  for (int i = 1; i < gn_model::kMaxLanes; ++i) {
+    if (m->lane_stream[i]) { cudaStreamSynchronize(m->lane_stream[i]); cudaStreamDestroy(m->lane_stream[i]); }
+    if (m->lane_join[i]) cudaEventDestroy(m->lane_join[i]);
+  }
+  if (m->lane_fork) cudaEventDestroy(m->lane_fork);
   for (void* p : m->owned)
     if (p) cudaFree(p);
   delete m;
@@ -913,6 +980,19 @@ int gn_forward_loss(gn_model* m, const int32_t* input_ids, const int32_t* labels
       GN_PROPAGATE(launch_logits_transpose(m->rows, logits + (int64_t)b0 * m->C * TS, nb, c.T, c.S, m->C, c.T, 0, st));
   }
   return GN_OK;
+}
+
+int gn_spatial_attention(const void* qkv, void* out, int n_frames, int S, int n_heads, int head_dim, float scale,
+                         int kernel, void* stream) {
+  GN_REQUIRE(qkv && out && n_frames > 0 && S > 0 && n_heads > 0 && head_dim > 0, "gn_spatial_attention: invalid argument");
+  AttnArgs aa{};
+  aa.qkv = qkv; aa.out = out; aa.act_bf16 = 1; aa.n_heads = n_heads; aa.head_dim = head_dim; aa.scale = scale;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (kernel == 1) {
+    GN_REQUIRE(fast_spatial_supported(aa, S), "mma.sync spatial kernel does not support this shape");
+    return fast_spatial_attention(aa, n_frames, S, st);
+  }
+  return launch_spatial_attention(aa, n_frames, S, kernel == 2, st);
 }
 
 int gn_linear_forward(const void* a, const void* w, const float* bias, const float* resid, void* out, void* out2, int M,

@@ -174,10 +174,13 @@ class STMaskGIT(nn.Module):
                         their 256-wide tile, so it is off by default)
       cuda_graphs       replay the per-chunk layer stack from a captured CUDA graph when running on a non-default
                         stream (default on)
+      lanes             number of concurrent streams the independent clips of a MaskGIT step are dealt to (0 = library
+                        default, 1 = single stream); bit-identical results for any value
     """
 
     def __init__(self, config: GenieConfig, precision: str = "bf16", kv_cache: bool = False, chunk_tokens: int = 0,
-                 generic_attention: bool = False, fold_ln: bool = False, cuda_graphs: bool = True):
+                 generic_attention: bool = False, fold_ln: bool = False, cuda_graphs: bool = True,
+                 lanes: int = 0):
         super().__init__()
         self.h = self.w = math.isqrt(config.S)
         assert self.h ** 2 == config.S, "Expected S to be square"
@@ -201,6 +204,7 @@ class STMaskGIT(nn.Module):
         self.generic_attention = bool(generic_attention)
         self.fold_ln = bool(fold_ln)
         self.cuda_graphs = bool(cuda_graphs)
+        self.lanes = int(lanes)
         self.__dict__["_native"] = None
         self.__dict__["_native_key"] = None
         self.__dict__["_weights_dirty"] = True
@@ -241,7 +245,7 @@ class STMaskGIT(nn.Module):
             mlp_ratio=float(c.mlp_ratio), precision=_lib.PRECISIONS[self.precision],
             chunk_tokens=self.chunk_tokens, kv_cache=int(self.kv_cache),
             generic_attention=int(self.generic_attention), fold_ln=int(self.fold_ln),
-            cuda_graphs=int(self.cuda_graphs))
+            cuda_graphs=int(self.cuda_graphs), lanes=self.lanes)
 
     def _handle(self) -> _NativeHandle:
         dev = self.device
@@ -250,7 +254,8 @@ class STMaskGIT(nn.Module):
                 "the GENIE B200 path runs on a CUDA device only (model is on "
                 f"{dev}); move it with .to('cuda').  There is no CPU fallback.")
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
-        key = (idx, self.precision, self.kv_cache, self.chunk_tokens, self.generic_attention, self.fold_ln, self.cuda_graphs)
+        key = (idx, self.precision, self.kv_cache, self.chunk_tokens, self.generic_attention, self.fold_ln, self.cuda_graphs,
+               self.lanes)
         d = self.__dict__
         if d["_native"] is None or d["_native_key"] != key:
             d["_native"] = _NativeHandle(self._gn_config(), idx)

@@ -201,6 +201,8 @@ def main():
     ap.add_argument("--chunk-tokens", type=int, default=32768)
     ap.add_argument("--fold-ln", action="store_true", help="LayerNorm folded into the QKV/fc1 GEMM epilogues")
     ap.add_argument("--no-graphs", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--lanes", type=int, default=0,
+                    help="concurrent streams the clips of a MaskGIT step are dealt to (0 = library default, 1 = single)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary (other mode) measurement")
     args = ap.parse_args()
@@ -229,7 +231,7 @@ def main():
 
     def make_model(mode):
         m = pkg.STMaskGIT(pkg.GenieConfig(**MODEL_KW), precision="bf16", kv_cache=(mode == "cached"),
-                          chunk_tokens=args.chunk_tokens, fold_ln=args.fold_ln, cuda_graphs=not args.no_graphs)
+                          chunk_tokens=args.chunk_tokens, fold_ln=args.fold_ln, cuda_graphs=not args.no_graphs, lanes=args.lanes)
         m.load_state_dict(sd)
         return m.to(dev)
 
@@ -355,7 +357,7 @@ def main():
                                    "(BASELINE.json configs[1])",
                        "clips_per_gpu": B, "prompt_frames": T_PROMPT, "new_frames": n_new,
                        "maskgit_steps": MASKGIT_STEPS, "frames_per_step": frames_per_step, "mode": args.mode,
-                       "kv_cache": args.mode == "cached", "precision": "bf16 operands, fp32 accumulate/residual",
+                       "kv_cache": args.mode == "cached", "lanes": args.lanes, "precision": "bf16 operands, fp32 accumulate/residual",
                        "cache_hygiene": "per-step working set (275 MB weights + >10 GB activations/KV) exceeds the "
                                         "126 MB L2; no L2 flush needed",
                        "parallelism": f"dp{world} (clips sharded, no collective)"},

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define GN_ABI_VERSION 2
+#define GN_ABI_VERSION 3
 
 /* precision modes of the linear layers / activations */
 #define GN_PREC_BF16 0 /* tcgen05 kind::f16, bf16 operands+activations, fp32 accumulate/residual/LN/softmax */
@@ -63,6 +63,11 @@ typedef struct gn_config {
   int32_t cuda_graphs;   /* 1: the per-chunk layer stack (~330 kernel launches) is captured once per shape into a CUDA
                             graph and replayed (only when the caller's stream is not the legacy default stream);
                             removes the host launch bound at small batch */
+  int32_t lanes;         /* clips are independent: the chunks of a MaskGIT step are dealt round-robin to this many
+                            concurrent streams (lane 0 = the caller's stream, the others library-owned, fork/join by
+                            events), each with its own workspace, so that one lane's HBM-bound kernels and GEMM tail
+                            waves overlap the other lane's tensor-bound kernels.  Results are bit-identical for any
+                            value.  0 = library default, 1 = single stream, max 4 */
 } gn_config;
 
 int gn_version(void);
@@ -130,6 +135,12 @@ int gn_forward_loss(gn_model* m, const int32_t* input_ids, const int32_t* labels
  * out2 (nullable) bf16 copy for epi 2; force_simt selects the CUDA-core kernel. */
 int gn_linear_forward(const void* a, const void* w, const float* bias, const float* resid, void* out, void* out2,
                       int M, int N, int K, int epi, int in_bf16, int out_bf16, int force_simt, void* stream);
+
+/* Test hook for the spatial attention kernels (the attention core of SelfAttention.forward, attention.py:48-58,
+ * non-causal): qkv [n_frames*S, 3*d] bf16 (column order (3, h, hd)) -> out [n_frames*S, d] bf16, d = n_heads*head_dim.
+ * kernel: 0 = library default (tcgen05 kernel when supported), 1 = mma.sync kernel, 2 = CUDA-core generic kernel. */
+int gn_spatial_attention(const void* qkv, void* out, int n_frames, int S, int n_heads, int head_dim, float scale,
+                         int kernel, void* stream);
 
 /* decode-step kernels exposed for isolated bit-exact tests against the oracle */
 /* uniform: nullptr = argmax; [R, NV] = inverse-CDF categorical draw (see gn_maskgit_generate) */

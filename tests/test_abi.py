@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 def test_python_binding_covers_header():
     pkg = importlib.import_module("1xgpt_b200")
     assert sorted(pkg._lib.SIGNATURES) == header_functions()
-    assert pkg._lib.load().gn_version() == 2
+    assert pkg._lib.load().gn_version() == 3
 
 
 def test_no_torch_types_in_abi():

@@ -254,3 +254,42 @@ def test_sample_tokens_categorical_inverse_cdf(lib):
                  (counts[~big].sum() - exp[~big].sum()) ** 2 / exp[~big].sum())
     dof = int(big.sum())
     assert abs(chi2 - dof) / math.sqrt(2 * dof) < 5
+
+
+def _spatial_ref(qkv, n_frames, S, H, hd, scale):
+    """softmax(q k^T * scale) v per (frame, head) in float64 from the bf16 inputs (attention.py:48-58, non-causal)."""
+    d = H * hd
+    x = qkv.double().reshape(n_frames, S, 3, H, hd).permute(2, 0, 3, 1, 4)      # [3, F, H, S, hd]
+    q, k, v = x[0], x[1], x[2]
+    p = torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1)
+    return (p @ v).permute(0, 2, 1, 3).reshape(n_frames * S, d)
+
+
+@pytest.mark.parametrize("n_frames,S,H,peaked", [(3, 256, 8, False), (2, 128, 8, False), (5, 256, 16, True),
+                                                  (1, 256, 2, True)])
+def test_spatial_attention_tcgen05(lib, n_frames, S, H, peaked):
+    """tcgen05 spatial attention (TMEM-resident scores, P fed to the PV MMA from TMEM, MN-major V operand) against a
+    float64 reference and against the mma.sync kernel it replaces.  `peaked`: large score range (exercises the
+    max-subtraction); each output element is a distinct mix of V rows, so a wrong key/column mapping cannot pass."""
+    L, _l = lib
+    hd = 64
+    d = H * hd
+    g = torch.Generator(device="cuda").manual_seed(100 + n_frames + S + H)
+    qkv = torch.randn(n_frames * S, 3 * d, device="cuda", generator=g)
+    if peaked:
+        qkv[:, :2 * d] *= 3.0
+    qkv = qkv.bfloat16().contiguous()
+    scale = 1.0 / math.sqrt(hd)
+    outs = []
+    for kernel in (0, 1):
+        out = torch.full((n_frames * S, d), float("nan"), device="cuda", dtype=torch.bfloat16)
+        _l.check(L.gn_spatial_attention(P(qkv), P(out), n_frames, S, H, hd, scale, kernel, None))
+        torch.cuda.synchronize()
+        outs.append(out)
+    ref = _spatial_ref(qkv, n_frames, S, H, hd, scale)
+    e_tc, e_mma = rel_fro(outs[0].double(), ref), rel_fro(outs[1].double(), ref)
+    print(f"spatial attention F={n_frames} S={S} H={H} peaked={peaked}: tcgen05 rel {e_tc:.3e}, mma.sync rel {e_mma:.3e}, "
+          f"max abs diff between kernels {float((outs[0].float() - outs[1].float()).abs().max()):.3e}")
+    assert torch.isfinite(outs[0].float()).all()
+    assert e_tc < 6e-3          # bf16 P and bf16 output rounding
+    assert e_tc < 1.5 * e_mma + 1e-3

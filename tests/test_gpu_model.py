@@ -304,6 +304,35 @@ def test_cuda_graph_replay_is_bit_identical():
     assert torch.equal(outs[False][1], outs[True][1])
 
 
+@pytest.mark.parametrize("graphs", [False, True])
+def test_lanes_are_bit_identical(graphs):
+    """lanes > 1 deals the (independent) clips of a MaskGIT step to concurrent streams with separate workspaces:
+    tokens and step-0 logits of a 3-frame autoregressive generation must equal the single-stream run bit for bit,
+    on the first call (graph capture on the lane streams) and on replays."""
+    z, kw, cfg, sd = _prod_setup("genie35m")
+    ids = torch.from_numpy(z["ids"]).long()
+    ids = torch.cat([ids, ids.flip(0), ids.roll(1, 2)], 0)[:5]      # 5 clips: uneven split over the lanes
+    B = ids.shape[0]
+    t_prompt = cfg.T - 3
+    noise = torch.stack([O.tie_free_noise(2, B, cfg.S, seed=31 + t) for t in range(3)])
+    side = torch.cuda.Stream()
+    outs = {}
+    for lanes in (1, 2, 3):
+        m = build_b200_model(kw, sd, precision="bf16", kv_cache=True, cuda_graphs=graphs, lanes=lanes)
+        runs = []
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                gen, lg = m.generate(ids[:, :t_prompt].reshape(B, -1).cuda(), None, max_new_tokens=3 * cfg.S,
+                                     maskgit_steps=2, temperature=0.0, noise=noise, return_logits=True)
+                side.synchronize()
+                runs.append((gen.cpu(), lg.cpu()))
+        assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
+        outs[lanes] = runs[0]
+    for lanes in (2, 3):
+        assert torch.equal(outs[1][0], outs[lanes][0])
+        assert torch.equal(outs[1][1], outs[lanes][1])
+
+
 def test_temporal_v2_matches_legacy_kernel(monkeypatch):
     """Temporal attention v2 (TMA-fed, K/V written into head-major caches by the QKV GEMM epilogue) against the
     legacy per-warp cp.async kernel (GENIE_B200_TEMPORAL_V2=0): same mma operands in the same tile positions, so the
