@@ -650,7 +650,7 @@ int gn_model_create(gn_model** out, const gn_config* cfg, int device) {
     probe.act_bf16 = m->act_bf16; probe.n_heads = cfg->num_heads; probe.head_dim = cfg->d_model / cfg->num_heads;
     m->tv2 = (on && !cfg->qk_norm && !cfg->generic_attention && temporal_v2_supported(probe, cfg->S, cfg->T)) ? 1 : 0;
   }
-  m->lanes = cfg->lanes <= 0 ? 2 : std::min<int>(cfg->lanes, gn_model::kMaxLanes);
+  m->lanes = cfg->lanes <= 0 ? 1 : std::min<int>(cfg->lanes, gn_model::kMaxLanes);   // measured neutral on B200: off by default
   m->hid = (int)(cfg->d_model * cfg->mlp_ratio);
   m->C = cfg->num_factored_vocabs * cfg->factored_vocab_size;
   m->layers.resize(cfg->num_layers);

@@ -265,12 +265,16 @@ def _spatial_ref(qkv, n_frames, S, H, hd, scale):
     return (p @ v).permute(0, 2, 1, 3).reshape(n_frames * S, d)
 
 
+@pytest.mark.parametrize("variant", ["2", "1"])
 @pytest.mark.parametrize("n_frames,S,H,peaked", [(3, 256, 8, False), (2, 128, 8, False), (5, 256, 16, True),
-                                                  (1, 256, 2, True)])
-def test_spatial_attention_tcgen05(lib, n_frames, S, H, peaked):
+                                                  (1, 256, 2, True), (47, 256, 8, False)])
+def test_spatial_attention_tcgen05(lib, monkeypatch, n_frames, S, H, peaked, variant):
     """tcgen05 spatial attention (TMEM-resident scores, P fed to the PV MMA from TMEM, MN-major V operand) against a
     float64 reference and against the mma.sync kernel it replaces.  `peaked`: large score range (exercises the
-    max-subtraction); each output element is a distinct mix of V rows, so a wrong key/column mapping cannot pass."""
+    max-subtraction); each output element is a distinct mix of V rows, so a wrong key/column mapping cannot pass.
+    variant 2 = persistent warp-specialised kernel (S = 256; 47 x 8 items > 148 CTAs exercises the stage ring and
+    the barrier phases over several items per CTA), 1 = one CTA per 128-query tile."""
+    monkeypatch.setenv("GENIE_B200_SPATIAL_TC", variant)
     L, _l = lib
     hd = 64
     d = H * hd
@@ -288,7 +292,7 @@ def test_spatial_attention_tcgen05(lib, n_frames, S, H, peaked):
         outs.append(out)
     ref = _spatial_ref(qkv, n_frames, S, H, hd, scale)
     e_tc, e_mma = rel_fro(outs[0].double(), ref), rel_fro(outs[1].double(), ref)
-    print(f"spatial attention F={n_frames} S={S} H={H} peaked={peaked}: tcgen05 rel {e_tc:.3e}, mma.sync rel {e_mma:.3e}, "
+    print(f"spatial attention variant {variant} F={n_frames} S={S} H={H} peaked={peaked}: tcgen05 rel {e_tc:.3e}, mma.sync rel {e_mma:.3e}, "
           f"max abs diff between kernels {float((outs[0].float() - outs[1].float()).abs().max()):.3e}")
     assert torch.isfinite(outs[0].float()).all()
     assert e_tc < 6e-3          # bf16 P and bf16 output rounding
