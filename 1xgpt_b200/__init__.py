@@ -16,10 +16,12 @@ from .model import (  # noqa: E402
     FactorizedEmbedding, ModelOutput, cosine_schedule,
 )
 from .vq import VQModel, VQConfig, decode_latents_wrapper  # noqa: E402
+from .synth import synthetic_state_dict  # noqa: E402
 from .factorization_utils import factorize_token_ids, unfactorize_token_ids, factorize_labels, nth_root  # noqa: E402
 
 __all__ = [
     "GenieConfig", "STMaskGIT", "STTransformerDecoder", "STBlock", "Mlp", "SelfAttention", "BasicSelfAttention",
     "MemoryEfficientAttention", "FactorizedEmbedding", "ModelOutput", "cosine_schedule", "factorize_token_ids",
     "unfactorize_token_ids", "factorize_labels", "nth_root", "GnError", "VQModel", "VQConfig", "decode_latents_wrapper",
+    "synthetic_state_dict",
 ]

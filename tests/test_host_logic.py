@@ -130,3 +130,17 @@ def test_raw_token_dataset_windows(tmp_path):
     with pytest.raises(NotImplementedError):
         os.remove(tmp_path / "segment_ids.bin")
         data.RawTokenDataset(tmp_path, window_size=4)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(num_layers=2, num_heads=2, d_model=64, num_factored_vocabs=2, qk_norm=False, qkv_bias=True),
+    dict(num_layers=1, num_heads=4, d_model=128, num_factored_vocabs=2, qk_norm=True, use_mup=True),
+])
+def test_synthetic_state_dict_equals_oracle_generator(kw):
+    """bench.py's B200 arm draws its random-init weights from the package (it may not import oracle/); the CPU
+    baseline legs use the oracle's generator: both must yield the same tensors, key for key."""
+    a = pkg.synthetic_state_dict(pkg.GenieConfig(**kw), seed=5, bias_std=0.02)
+    b = O.init_state_dict(O.OracleConfig(**kw), seed=5, bias_std=0.02)
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
