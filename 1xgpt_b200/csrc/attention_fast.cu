@@ -475,7 +475,8 @@ __device__ __forceinline__ uint32_t line_off(int line, int c) {      // SWIZZLE_
 __global__ void __launch_bounds__(576, 1)
 temporal_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, int n_pos,
-                        int S, int H, int t0, int Tq, int n_stages, int rq_bytes, int rk_bytes, float scale_log2e) {
+                        int S, int H, int t0, int Tq, int n_stages, int rq_bytes, int rk_bytes, float scale_log2e,
+                        int hint) {
   constexpr int HD = 64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -506,14 +507,20 @@ temporal_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     // ------------------------------------------------------------------ TMA producer (one thread)
     if (lane == 0) {
       const uint32_t tx = (uint32_t)(Tq + 2 * Tk) * H * (HD * 2);
+      const uint64_t pol = l2_policy_evict_first();
       auto issue = [&](int j, int st) {
         const int pos = blockIdx.x + j * gridDim.x;
         const int b = pos / S, sp = pos - b * S;
         uint8_t* base = smem + st * stage_bytes;
         mbar_arrive_expect_tx(&full_bar[st], tx);
         tma_load_4d(base, &tmQ, &full_bar[st], 0, 0, sp, b * Tq);
-        tma_load_3d(base + rq_bytes, &tmK, &full_bar[st], 0, 0, pos * H);
-        tma_load_3d(base + rq_bytes + rk_bytes, &tmV, &full_bar[st], 0, 0, pos * H);
+        if (hint) {   // the K/V cache is a pure stream (hundreds of MB per launch): do not let it flush L2
+          tma_load_3d_hint(base + rq_bytes, &tmK, &full_bar[st], 0, 0, pos * H, pol);
+          tma_load_3d_hint(base + rq_bytes + rk_bytes, &tmV, &full_bar[st], 0, 0, pos * H, pol);
+        } else {
+          tma_load_3d(base + rq_bytes, &tmK, &full_bar[st], 0, 0, pos * H);
+          tma_load_3d(base + rq_bytes + rk_bytes, &tmV, &full_bar[st], 0, 0, pos * H);
+        }
       };
       for (int j = 0; j < n_stages && j < n_my; ++j) issue(j, j);
       int st = 0;
@@ -676,8 +683,10 @@ int launch_temporal_v2(const AttnArgs& a, int nb, int S, int T, int t0, int Tq, 
     if (sms <= 0) sms = 148;
   }
   const int grid = std::min(n_pos, sms * per_sm);
+  const char* he = getenv("GENIE_B200_KV_HINT");   // 0: plain loads of the K/V cache (A/B measurements)
+  const int hint = !(he && he[0] == '0');
   GN_CUDA_CHECK(launch_kernel(PC_TEMPORAL, kern, dim3(grid), dim3((H + 1) * 32), (size_t)smem, st, tmQ, tmK, tmV, tmO,
-                              n_pos, S, H, t0, Tq, ns, rq, rk, a.scale * 1.4426950408889634f));
+                              n_pos, S, H, t0, Tq, ns, rq, rk, a.scale * 1.4426950408889634f, hint));
   ++g_launch_count;
   return GN_OK;
 }

@@ -331,6 +331,7 @@ spatial_attn_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmKV, cons
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      const uint64_t pol = l2_policy_evict_first();
       for (int i = 0; i < n_my; ++i) {
         const int item = (int)blockIdx.x + i * (int)gridDim.x;
         const int f = item / n_heads, h = item % n_heads;
@@ -338,9 +339,10 @@ spatial_attn_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmKV, cons
         uint8_t* st = smem + s * TCP_STAGE_BYTES;
         mbar_wait(&bars->empty[s], ((i >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&bars->full[s], TCP_STAGE_BYTES);
-        tma_load_2d(st, &tmKV, &bars->full[s], h * TCA_HD, f * SK);                              // Q, 256 rows
-        tma_load_2d(st + SK * TCA_ROWB, &tmKV, &bars->full[s], d + h * TCA_HD, f * SK);          // K
-        tma_load_2d(st + 2 * SK * TCA_ROWB, &tmKV, &bars->full[s], 2 * d + h * TCA_HD, f * SK);  // V
+        // the fused QKV rows are read exactly once (by this kernel): evict_first
+        tma_load_2d_hint(st, &tmKV, &bars->full[s], h * TCA_HD, f * SK, pol);                              // Q, 256 rows
+        tma_load_2d_hint(st + SK * TCA_ROWB, &tmKV, &bars->full[s], d + h * TCA_HD, f * SK, pol);          // K
+        tma_load_2d_hint(st + 2 * SK * TCA_ROWB, &tmKV, &bars->full[s], 2 * d + h * TCA_HD, f * SK, pol);  // V
       }
     }
   } else if (warp == 1) {

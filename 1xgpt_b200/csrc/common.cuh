@@ -63,6 +63,19 @@ void prof_before(int cat, cudaStream_t st);
 void prof_after(cudaStream_t st);
 extern bool g_prof_on;
 
+// L2 residency of the fp32 residual stream.  While a window is set (model.cu sets it around the layer stack of a
+// chunk), every kernel launch carries cudaLaunchAttributeAccessPolicyWindow for that address range with the
+// "persisting" property: the stream is read and rewritten by 3 residual GEMMs and read by 2 LayerNorm passes per block,
+// so keeping it in the L2 set-aside removes most of its HBM traffic (the wide activations - QKV, MLP hidden - stream
+// through the rest of L2).  num_bytes == 0: no attribute.
+extern cudaAccessPolicyWindow g_l2_window;
+inline int add_l2_window_attr(cudaLaunchAttribute* attr, int n) {
+  if (g_l2_window.num_bytes == 0) return n;
+  attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
+  attr[n].val.accessPolicyWindow = g_l2_window;
+  return n + 1;
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(int cat, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                  Args&&... args) {
@@ -72,11 +85,16 @@ inline cudaError_t launch_kernel(int cat, void (*kern)(KArgs...), dim3 grid, dim
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (g_use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  na = add_l2_window_attr(attr, na);
   cfg.attrs = attr;
-  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cfg.numAttrs = na;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
   if (g_prof_on) prof_after(st);
   return e;
@@ -92,15 +110,21 @@ inline cudaError_t launch_kernel_cluster(int cat, void (*kern)(KArgs...), dim3 g
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cluster_x;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[3];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = cluster_x;
+  attr[na].val.clusterDim.y = 1;
+  attr[na].val.clusterDim.z = 1;
+  ++na;
+  if (g_use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  na = add_l2_window_attr(attr, na);
   cfg.attrs = attr;
-  cfg.numAttrs = g_use_pdl ? 2 : 1;
+  cfg.numAttrs = na;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
   if (g_prof_on) prof_after(st);
   return e;

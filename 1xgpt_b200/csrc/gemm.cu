@@ -88,6 +88,7 @@ struct TcArgs {
   // profiling aid (GENIE_B200_GEMM_DEBUG; results are garbage): bit 0 = store/GELU epilogues release the accumulator
   // without reading or storing it, bit 1 = the producer signals the stages without loading them
   int dbg;
+  int a_hint;   // 1: the A operand is dead after this GEMM -> load it with the L2 evict_first policy
 };
 
 template <typename OutT>
@@ -191,6 +192,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      const uint64_t pol = l2_policy_evict_first();
+      const bool a_hint = args.a_hint != 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int m_blk = tile / num_n, n_blk = tile % num_n;
         const int m_row0 = (m_blk * CTAS + (int)cta_rank) * BLOCK_M;
@@ -205,7 +208,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // both CTAs' bytes complete on the LEADER's barrier (which the MMA issuer waits on)
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * SM::STAGE_BYTES);
             const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
-            tma_load_2d_pair(smem_a + stage * A_TILE_BYTES, &tmA, bar, kb * BLOCK_K, m_row0);
+            if (a_hint) tma_load_2d_pair_hint(smem_a + stage * A_TILE_BYTES, &tmA, bar, kb * BLOCK_K, m_row0, pol);
+            else tma_load_2d_pair(smem_a + stage * A_TILE_BYTES, &tmA, bar, kb * BLOCK_K, m_row0);
             tma_load_2d_pair(smem_b + stage * SM::B_TILE_BYTES, &tmB, bar, kb * BLOCK_K,
                              n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / 2));
           } else {
@@ -219,6 +223,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               const int tap = kb / args.cin_blocks, cib = kb % args.cin_blocks;
               tma_load_4d(smem_a + stage * A_TILE_BYTES, &tmA, &full_bar[stage], cib * BLOCK_K,
                           x0 * args.stride + tap % 3 - 1, y0 * args.stride + tap / 3 - 1, n);
+            } else if (a_hint) {
+              tma_load_2d_hint(smem_a + stage * A_TILE_BYTES, &tmA, &full_bar[stage], kb * BLOCK_K, m_row0, pol);
             } else {
               tma_load_2d(smem_a + stage * A_TILE_BYTES, &tmA, &full_bar[stage], kb * BLOCK_K, m_row0);
             }
@@ -601,6 +607,7 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
     const char* e = getenv("GENIE_B200_GEMM_DEBUG");   // re-read per launch: scripts/gemm_ablation.py flips it
     t.dbg = e ? atoi(e) : 0;
   }
+  t.a_hint = a.a_evict_first;
   if (kv) { t.kv_d = a.kv_d; t.kv_hd = a.kv_hd; t.kv_S = a.kv_S; t.kv_Tact = a.kv_Tact; t.kv_t0 = a.kv_t0; }
   if (a.conv) {
     t.cin_blocks = a.conv->Cin / BLOCK_K;

@@ -44,6 +44,7 @@ struct LinearArgs {
   int out_bf16;       // 1: out is bf16, 0: f32
   int force_simt;     // 1: CUDA-core fp32 path regardless of shape
   int round_out_tf32; // 1: round the fp32 output to tf32 (it feeds a kind::tf32 GEMM next)
+  int a_evict_first;  // 1: A is not read again after this GEMM (L2 evict_first hint on its loads)
   const ConvGeom* conv; // non-null: implicit-GEMM 3x3 convolution (A = NHWC input, K = 9*Cin, M = Nimg*Ho*Wo)
   // LayerNorm folded into the epilogue (A holds the RAW bf16 rows, W holds W*diag(gamma)):
   //   out[m,n] = rstd[m] * (acc[m,n] - mean[m] * colsum[n]) + bias[n]        (bias already contains beta . W^T)
