@@ -37,9 +37,12 @@ constexpr int MAX_EPI_WARPS = 8;
 constexpr int MAX_GEMM_THREADS = 32 * (2 + MAX_EPI_WARPS);
 constexpr int SMEM_LIMIT = 232448;           // 227 KB opt-in dynamic shared memory per CTA
 
-constexpr int RES_BUFS = 4;      // residual epilogue: in-place staging buffers per warp (3 for 256-wide tiles that also
-                                 // emit the bf16 copy, so that a 3-stage operand ring still fits)
-constexpr int res_bufs(int block_n, bool dual) { return (block_n > 128 && dual) ? 3 : RES_BUFS; }
+// Residual epilogue: in-place staging buffers per warp (4 KB each); RB - 2 residual chunks are requested ahead of use.
+// 4 buffers (3 for 256-wide tiles that also emit the bf16 copy, so that a 3-stage operand ring still fits).  A deeper
+// residual ring (6 / 5 buffers) was measured SLOWER (proj 50.8 -> 56.5 us, fc2 83 -> 91 us at M = 32768): it costs one
+// operand stage, and the operand ring is what keeps the L2 -> SM stream busy.
+constexpr int RES_BUFS = 4;
+constexpr int res_bufs(int block_n, bool dual, int /*ctas*/) { return (block_n > 128 && dual) ? 3 : RES_BUFS; }
 
 // CTAS = 2: CTA-pair tiles (tcgen05 cta_group::2).  One tile is 256 rows x BLOCK_N columns; each CTA of the pair stages
 // its own 128 rows of A and ONE HALF of the B tile, so a k-block costs A + B/2 bytes of L2->SM traffic per SM instead
@@ -54,7 +57,7 @@ struct GemmSmem {
   static constexpr int EPI_BUF_BYTES = 32 * EPI_COLS * (int)sizeof(OutT);
   static constexpr int STORE_BUFS = (COLS_PER_WARP / EPI_COLS) * EPI_BUF_BYTES <= 8192
                                         ? COLS_PER_WARP / EPI_COLS : 8192 / EPI_BUF_BYTES;
-  static constexpr int OUT_BUFS = EPI == EPI_RESID ? res_bufs(BLOCK_N, DUAL) : STORE_BUFS;
+  static constexpr int OUT_BUFS = EPI == EPI_RESID ? res_bufs(BLOCK_N, DUAL, CTAS) : STORE_BUFS;
   static constexpr int B_TILE_BYTES = (BLOCK_N / CTAS) * TILE_K_BYTES;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int OUT_STAGE_BYTES = 32 * EPI_COLS * (int)sizeof(OutT);          // per warp per buffer
@@ -371,17 +374,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(&acc_full[as], aphase);
         tc_fence_after();
         float rs1 = 0.f, rs2 = 0.f;   // partial {sum, sumsq} of this thread's row over the tile's columns
-#pragma unroll 1
-        for (int c = 0; c < CH; ++c, ++g) {
+        const uint32_t acc_addr = tmem_base + ((q * 32u) << 16) + as * BLOCK_N;
+        uint32_t rr[2][EPI_COLS];
+        tmem_ld_32x32b_x32(acc_addr, rr[0]);
+        // one chunk: wait for its TMEM load and start the next chunk's load (it overlaps the residual read-modify-write
+        // below), then acc + bias + residual in place in the staging buffer, TMA store
+        auto do_chunk = [&](uint32_t (&r)[EPI_COLS], uint32_t (&rnext)[EPI_COLS], int c) {
           const int col0 = n_blk * BLOCK_N + c * EPI_COLS;
           if (lane == 0) {
             // buffer (g + RP) % RB was last stored from RB - RP chunks ago
             tma_store_wait_read<RB - RP - 1>();
             if (g + RP < total_chunks) issue_residual(g + RP);
           }
-          uint32_t r[EPI_COLS];
-          tmem_ld_32x32b_x32(tmem_base + ((q * 32u) << 16) + as * BLOCK_N + c * EPI_COLS, r);
           tmem_ld_wait();
+          if (c + 1 < CH) tmem_ld_32x32b_x32(acc_addr + (c + 1) * EPI_COLS, rnext);
           if (c == CH - 1) {
             tc_fence_before();
             __syncwarp();
@@ -414,6 +420,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (DUAL) tma_store_2d(&tmOut2, st1 + (g & 1) * SM::OUT2_STAGE_BYTES, col0, row0);
             tma_store_commit();
           }
+          ++g;
+        };
+#pragma unroll 1
+        for (int c2 = 0; c2 < CH; c2 += 2) {
+          do_chunk(rr[0], rr[1], c2);
+          if (c2 + 1 < CH) do_chunk(rr[1], rr[0], c2 + 1);
         }
         if (args.stats_out != nullptr && row0 + (int)lane < args.M) {
           reinterpret_cast<float2*>(args.stats_out)[(int64_t)(row0 + lane) * num_n + n_blk] = make_float2(rs1, rs2);
