@@ -672,7 +672,8 @@ int dispatch_n(const LinearArgs& a, cudaStream_t s) {
   const bool pair = env_on("GENIE_B200_PAIR", g_use_pair) && !a.conv && a.M > BLOCK_M;
   if (a.N % 256 == 0 && pair && (a.epi != EPI_RESID || a.K >= 1024 || env_on("GENIE_B200_PAIR_PROJ", false)))
     return dispatch_epi<InT, 256, 2>(a, s);
-  if (a.N % 256 == 0 && (a.epi != EPI_RESID || a.K >= 1024)) return dispatch_epi<InT, 256>(a, s);
+  if (a.N % 256 == 0 && (a.epi != EPI_RESID || a.K >= 1024 || env_on("GENIE_B200_PROJ256", false)))
+    return dispatch_epi<InT, 256>(a, s);
   if (a.N % 128 == 0) return dispatch_epi<InT, 128>(a, s);
   return dispatch_epi<InT, 64>(a, s);
 }
