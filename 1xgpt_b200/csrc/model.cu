@@ -719,6 +719,8 @@ void gn_model_destroy(gn_model* m) {
   if (m->lane_fork) cudaEventDestroy(m->lane_fork);
   for (void* p : m->owned)
     if (p) cudaFree(p);
+  cudaCtxResetPersistingL2Cache();   // lines of the (now freed) residual stream leave the L2 set-aside
+  cudaGetLastError();
   delete m;
 }
 
