@@ -9,12 +9,21 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import magvit_oracle as MO  # weights only (seeded init)
 
 pkg = importlib.import_module("1xgpt_b200")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 m = pkg.VQModel()
-m.load_state_dict(MO.init_vq_state_dict(MO.VQOracleConfig(), seed=31))
+# seeded synthetic weights (no checkpoint reachable): fan-in scaled convs, GroupNorm affine near identity
+_g = torch.Generator().manual_seed(31)
+_sd = {}
+for _k, _v in m.state_dict().items():
+    if _v.dim() == 4:
+        _sd[_k] = torch.randn(_v.shape, generator=_g) / (_v.shape[1] * _v.shape[2] * _v.shape[3]) ** 0.5
+    elif "norm" in _k and _k.endswith(".weight"):
+        _sd[_k] = 1.0 + 0.1 * torch.randn(_v.shape, generator=_g)
+    else:
+        _sd[_k] = 0.05 * torch.randn(_v.shape, generator=_g)
+m.load_state_dict(_sd)
 m = m.to("cuda")
 img = (torch.rand(B, 3, 256, 256, generator=torch.Generator().manual_seed(7)) * 2 - 1).cuda()
 
