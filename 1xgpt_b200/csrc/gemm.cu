@@ -54,13 +54,20 @@ struct GemmSmem {
   static constexpr int COLS_PER_WARP = BLOCK_N / (NUM_EPI_WARPS / 4);   // columns of the tile one warp handles
   // store / GELU epilogues: one staging buffer per 32-column chunk of the warp's slice (8 KB per warp), so a buffer is
   // rewritten a whole tile after its TMA store was issued and the store's read latency never stalls the warp
-  static constexpr int EPI_BUF_BYTES = 32 * EPI_COLS * (int)sizeof(OutT);
-  static constexpr int STORE_BUFS = (COLS_PER_WARP / EPI_COLS) * EPI_BUF_BYTES <= 8192
-                                        ? COLS_PER_WARP / EPI_COLS : 8192 / EPI_BUF_BYTES;
+  // bf16 outputs of the store / GELU epilogues: two 32-column chunks are staged side by side (128 B per row = one
+  // 128B-swizzle atom) and leave as ONE TMA store of 32 rows x 64 columns: full 128-byte lines instead of 64-byte
+  // halves (for the temporal K/V caches: one (position, head, frame) row of head_dim 64 per line) and half as many
+  // bulk stores per tile
+  static constexpr bool WIDE = EPI != EPI_RESID && sizeof(OutT) == 2 && COLS_PER_WARP % (2 * EPI_COLS) == 0;
+  static constexpr int EPI_BUF_BYTES = 32 * EPI_COLS * (int)sizeof(OutT) * (WIDE ? 2 : 1);
+  static constexpr int CHUNKS_PER_BUF = WIDE ? 2 : 1;
+  static constexpr int STORE_BUFS_RAW = (COLS_PER_WARP / (EPI_COLS * CHUNKS_PER_BUF)) * EPI_BUF_BYTES <= 8192
+                                            ? COLS_PER_WARP / (EPI_COLS * CHUNKS_PER_BUF) : 8192 / EPI_BUF_BYTES;
+  static constexpr int STORE_BUFS = (WIDE && STORE_BUFS_RAW < 2) ? 2 : STORE_BUFS_RAW;
   static constexpr int OUT_BUFS = EPI == EPI_RESID ? res_bufs(BLOCK_N, DUAL, CTAS) : STORE_BUFS;
   static constexpr int B_TILE_BYTES = (BLOCK_N / CTAS) * TILE_K_BYTES;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int OUT_STAGE_BYTES = 32 * EPI_COLS * (int)sizeof(OutT);          // per warp per buffer
+  static constexpr int OUT_STAGE_BYTES = EPI == EPI_RESID ? 32 * EPI_COLS * (int)sizeof(OutT) : EPI_BUF_BYTES;  // per warp per buffer
   static constexpr int OUT2_STAGE_BYTES = DUAL ? 32 * EPI_COLS * 2 : 0;
   static constexpr int STAGING_BYTES = NUM_EPI_WARPS * (OUT_BUFS * OUT_STAGE_BYTES + 2 * OUT2_STAGE_BYTES);
   static constexpr int BIAS_BYTES = 2 * NUM_EPI_WARPS * COLS_PER_WARP * 4;   // per-warp copies of its slice of the
@@ -119,6 +126,20 @@ __device__ __forceinline__ void stage_row_chunk<bf16>(uint8_t* buf, uint32_t lan
     p.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
     p.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
     *reinterpret_cast<uint4*>(row + ((j ^ ((lane >> 1) & 3)) << 4)) = p;
+  }
+}
+
+// bf16, wide staging: 64 cols = 128 B per row, SWIZZLE_128B; `half` selects the left / right 32 columns
+__device__ __forceinline__ void stage_row_chunk_wide(uint8_t* buf, uint32_t lane, int half, const float (&v)[EPI_COLS]) {
+  uint8_t* row = buf + lane * 128;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 p;
+    p.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+    p.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+    p.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+    p.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+    *reinterpret_cast<uint4*>(row + (((half * 4 + j) ^ (lane & 7)) << 4)) = p;
   }
 }
 
@@ -487,24 +508,51 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < EPI_COLS; ++j) v[j] = tf32_rn(v[j]);
           }
-          // the staging buffer about to be written was last stored from OUT_BUFS steps ago
-          if (lane == 0) tma_store_wait_read<SM::OUT_BUFS - 1>();
-          __syncwarp();
-          if (!(args.dbg & 8)) stage_row_chunk<OutT>(st0 + buf * SM::OUT_STAGE_BYTES, lane, v);
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0 && !(args.dbg & 4)) {
-            if (EPI == EPI_STORE && sizeof(OutT) == 2 && args.kv_d > 0 && col0 >= args.kv_d) {
-              const int part = col0 >= 2 * args.kv_d ? 2 : 1;
-              const int cc = col0 - part * args.kv_d;
-              tma_store_4d(part == 1 ? &tmK : &tmV, st0 + buf * SM::OUT_STAGE_BYTES, cc % args.kv_hd, kv_frame,
-                           cc / args.kv_hd, kv_pos);
-            } else {
-              tma_store_2d(&tmOut, st0 + buf * SM::OUT_STAGE_BYTES, col0, row0);
+          if constexpr (SM::WIDE) {
+            const int half = c & 1;
+            // the staging buffer about to be written was last stored from OUT_BUFS stores ago
+            if (half == 0) {
+              if (lane == 0) tma_store_wait_read<SM::OUT_BUFS - 1>();
+              __syncwarp();
             }
-            tma_store_commit();
+            if (!(args.dbg & 8)) stage_row_chunk_wide(st0 + buf * SM::OUT_STAGE_BYTES, lane, half, v);
+            if (half == 1) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              const int colp = col0 - EPI_COLS;   // first column of the pair
+              if (lane == 0 && !(args.dbg & 4)) {
+                if (EPI == EPI_STORE && args.kv_d > 0 && colp >= args.kv_d) {
+                  const int part = colp >= 2 * args.kv_d ? 2 : 1;
+                  const int cc = colp - part * args.kv_d;
+                  tma_store_4d(part == 1 ? &tmK : &tmV, st0 + buf * SM::OUT_STAGE_BYTES, cc % args.kv_hd, kv_frame,
+                               cc / args.kv_hd, kv_pos);
+                } else {
+                  tma_store_2d(&tmOut, st0 + buf * SM::OUT_STAGE_BYTES, colp, row0);
+                }
+                tma_store_commit();
+              }
+              buf = (buf + 1 == SM::OUT_BUFS) ? 0 : buf + 1;
+            }
+          } else {
+            // the staging buffer about to be written was last stored from OUT_BUFS steps ago
+            if (lane == 0) tma_store_wait_read<SM::OUT_BUFS - 1>();
+            __syncwarp();
+            if (!(args.dbg & 8)) stage_row_chunk<OutT>(st0 + buf * SM::OUT_STAGE_BYTES, lane, v);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && !(args.dbg & 4)) {
+              if (EPI == EPI_STORE && sizeof(OutT) == 2 && args.kv_d > 0 && col0 >= args.kv_d) {
+                const int part = col0 >= 2 * args.kv_d ? 2 : 1;
+                const int cc = col0 - part * args.kv_d;
+                tma_store_4d(part == 1 ? &tmK : &tmV, st0 + buf * SM::OUT_STAGE_BYTES, cc % args.kv_hd, kv_frame,
+                             cc / args.kv_hd, kv_pos);
+              } else {
+                tma_store_2d(&tmOut, st0 + buf * SM::OUT_STAGE_BYTES, col0, row0);
+              }
+              tma_store_commit();
+            }
+            if (SM::OUT_BUFS > 1) buf = (buf + 1 == SM::OUT_BUFS) ? 0 : buf + 1;
           }
-          if (SM::OUT_BUFS > 1) buf = (buf + 1 == SM::OUT_BUFS) ? 0 : buf + 1;
         };
 #pragma unroll 1
         for (int c2 = 0; c2 < CH; c2 += 2) {
@@ -547,8 +595,10 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
                                   CU_TENSOR_MAP_SWIZZLE_128B));
   GN_PROPAGATE(make_tensor_map_2d(&tmB, a.W, in_dt, sizeof(InT), a.K, a.N, a.ldw, BLOCK_K, BLOCK_N / CTAS,
                                   CU_TENSOR_MAP_SWIZZLE_128B));
-  GN_PROPAGATE(make_tensor_map_2d(&tmO, a.out, out_dt, sizeof(OutT), a.N, a.M, a.ldo, EPI_COLS, 32,
-                                  sizeof(OutT) == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B));
+  GN_PROPAGATE(make_tensor_map_2d(&tmO, a.out, out_dt, sizeof(OutT), a.N, a.M, a.ldo,
+                                  SM::WIDE ? 2 * EPI_COLS : EPI_COLS, 32,
+                                  (sizeof(OutT) == 2 && !SM::WIDE) ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                   : CU_TENSOR_MAP_SWIZZLE_128B));
   if (DUAL) {
     GN_PROPAGATE(make_tensor_map_2d(&tmO2, a.out2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.N, a.M, a.ldo2, EPI_COLS,
                                     32, CU_TENSOR_MAP_SWIZZLE_64B));
@@ -567,11 +617,15 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
     const int H = a.kv_d / a.kv_hd;
     const int64_t dims[4] = {a.kv_hd, a.kv_T, H, (int64_t)a.kv_clips * a.kv_S};
     const int64_t str[3] = {(int64_t)a.kv_hd * 2, (int64_t)a.kv_T * a.kv_hd * 2, (int64_t)H * a.kv_T * a.kv_hd * 2};
-    const int box[4] = {EPI_COLS, 1, 1, 32};
-    GN_PROPAGATE(make_tensor_map_nd(&tmK, a.kv_k, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, str, box,
-                                    CU_TENSOR_MAP_SWIZZLE_64B));
-    GN_PROPAGATE(make_tensor_map_nd(&tmV, a.kv_v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, str, box,
-                                    CU_TENSOR_MAP_SWIZZLE_64B));
+    // wide staging: one store = 32 positions x one full head (64 columns = 128 B) of one frame
+    if (SM::WIDE && a.kv_hd != 2 * EPI_COLS) {
+      set_error("K/V-cache epilogue with wide staging needs head_dim %d (got %d)", 2 * EPI_COLS, a.kv_hd);
+      return GN_ERR_UNSUPPORTED;
+    }
+    const int box[4] = {SM::WIDE ? 2 * EPI_COLS : EPI_COLS, 1, 1, 32};
+    const CUtensorMapSwizzle ksw = SM::WIDE ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    GN_PROPAGATE(make_tensor_map_nd(&tmK, a.kv_k, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, str, box, ksw));
+    GN_PROPAGATE(make_tensor_map_nd(&tmV, a.kv_v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, str, box, ksw));
   } else {
     tmK = tmO;
     tmV = tmO;
