@@ -99,6 +99,7 @@ struct TcArgs {
   // without reading or storing it, bit 1 = the producer signals the stages without loading them
   int dbg;
   int a_hint;   // 1: the A operand is dead after this GEMM -> load it with the L2 evict_first policy
+  int w_prefetch;   // 1: pull this CTA's first weight tiles into L2 before griddepcontrol.wait
 };
 
 template <typename OutT>
@@ -209,7 +210,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched only below
+  // Optional (GENIE_B200_W_PREFETCH=1, off: measured neutral to slightly negative).  The weights are not produced by
+  // the preceding kernel, so their first tiles may be requested while that kernel is still draining (PDL): by the
+  // time the dependency resolves, the B operand of every CTA's first tile is in L2.
+  if (args.w_prefetch && warp == 0 && lane == 0 && pair < num_tiles) {
+    const int n_blk0 = pair % num_n;
+    const int kbs = num_kb < 32 ? num_kb : 32;
+    for (int kb = 0; kb < kbs; ++kb)
+      tma_prefetch_l2_2d(&tmB, kb * BLOCK_K, n_blk0 * BLOCK_N + (int)cta_rank * (BLOCK_N / CTAS));
+  }
+  pdl_wait();      // everything above overlapped the previous kernel's tail; activations are touched only below
   pdl_trigger();
 
   if (warp == 0) {
@@ -674,6 +684,7 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
     t.dbg = e ? atoi(e) : 0;
   }
   t.a_hint = a.a_evict_first;
+  t.w_prefetch = env_on("GENIE_B200_W_PREFETCH", false) ? 1 : 0;   // measured: 257.9 vs 257.3 ms per step -> off
   if (kv) { t.kv_d = a.kv_d; t.kv_hd = a.kv_hd; t.kv_S = a.kv_S; t.kv_Tact = a.kv_Tact; t.kv_t0 = a.kv_t0; }
   if (a.conv) {
     t.cin_blocks = a.conv->Cin / BLOCK_K;
