@@ -100,6 +100,9 @@ struct TcArgs {
   int dbg;
   int a_hint;   // 1: the A operand is dead after this GEMM -> load it with the L2 evict_first policy
   int w_prefetch;   // 1: pull this CTA's first weight tiles into L2 before griddepcontrol.wait
+  const float* qkn_g;   // qk-LayerNorm over 64-column groups of output columns [0, qkn_cols) (wide bf16 store epilogue)
+  const float* qkn_b;
+  int qkn_cols;
 };
 
 template <typename OutT>
@@ -144,7 +147,7 @@ __device__ __forceinline__ void stage_row_chunk_wide(uint8_t* buf, uint32_t lane
   }
 }
 
-template <typename InT, int BLOCK_N, int EPI, typename OutT, bool DUAL, int CTAS>
+template <typename InT, int BLOCK_N, int EPI, typename OutT, bool DUAL, int CTAS, bool QKN>
 __global__ void __launch_bounds__(32 * (2 + EpiCfg<EPI>::WARPS), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
@@ -488,6 +491,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           kv_pos = (bt / args.kv_Tact) * args.kv_S + row0 % args.kv_S;
         }
         uint32_t rr[2][EPI_COLS];
+        float vsave[QKN ? EPI_COLS : 1];   // first half of a 64-column pair, kept for the qk-LayerNorm of the pair
         tmem_ld_32x32b_x32(acc_addr, rr[0]);
         // one chunk: wait for its TMEM load, start the next chunk's load (overlaps the math), bias / activation,
         // swizzled staging, TMA store
@@ -525,7 +529,48 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (lane == 0) tma_store_wait_read<SM::OUT_BUFS - 1>();
               __syncwarp();
             }
-            if (!(args.dbg & 8)) stage_row_chunk_wide(st0 + buf * SM::OUT_STAGE_BYTES, lane, half, v);
+            // qk-LayerNorm: the two chunks of a pair are the 64 columns of one head of this thread's row
+            const bool qkn = QKN && (col0 - half * EPI_COLS) < args.qkn_cols;
+            if constexpr (!QKN) {
+              if (!(args.dbg & 8)) stage_row_chunk_wide(st0 + buf * SM::OUT_STAGE_BYTES, lane, half, v);
+            } else if (qkn) {
+              if (half == 0) {
+#pragma unroll
+                for (int j = 0; j < EPI_COLS; ++j) vsave[j] = v[j];
+              } else {
+                float s1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < EPI_COLS; ++j) s1 += vsave[j] + v[j];
+                const float mean = s1 * (1.f / (2 * EPI_COLS));
+                float s2 = 0.f;
+#pragma unroll
+                for (int j = 0; j < EPI_COLS; ++j) {
+                  const float d0 = vsave[j] - mean, d1 = v[j] - mean;
+                  s2 = fmaf(d0, d0, s2);
+                  s2 = fmaf(d1, d1, s2);
+                }
+                const float rstd = rsqrtf(s2 * (1.f / (2 * EPI_COLS)) + 1e-5f);
+                const float4* g4 = reinterpret_cast<const float4*>(args.qkn_g);
+                const float4* b4 = reinterpret_cast<const float4*>(args.qkn_b);
+#pragma unroll
+                for (int j = 0; j < EPI_COLS / 4; ++j) {
+                  const float4 ga = __ldg(g4 + j), ba = __ldg(b4 + j);
+                  const float4 gb = __ldg(g4 + EPI_COLS / 4 + j), bb = __ldg(b4 + EPI_COLS / 4 + j);
+                  vsave[4 * j] = (vsave[4 * j] - mean) * rstd * ga.x + ba.x;
+                  vsave[4 * j + 1] = (vsave[4 * j + 1] - mean) * rstd * ga.y + ba.y;
+                  vsave[4 * j + 2] = (vsave[4 * j + 2] - mean) * rstd * ga.z + ba.z;
+                  vsave[4 * j + 3] = (vsave[4 * j + 3] - mean) * rstd * ga.w + ba.w;
+                  v[4 * j] = (v[4 * j] - mean) * rstd * gb.x + bb.x;
+                  v[4 * j + 1] = (v[4 * j + 1] - mean) * rstd * gb.y + bb.y;
+                  v[4 * j + 2] = (v[4 * j + 2] - mean) * rstd * gb.z + bb.z;
+                  v[4 * j + 3] = (v[4 * j + 3] - mean) * rstd * gb.w + bb.w;
+                }
+                stage_row_chunk_wide(st0 + buf * SM::OUT_STAGE_BYTES, lane, 0, vsave);
+                stage_row_chunk_wide(st0 + buf * SM::OUT_STAGE_BYTES, lane, 1, v);
+              }
+            } else if (!(args.dbg & 8)) {
+              stage_row_chunk_wide(st0 + buf * SM::OUT_STAGE_BYTES, lane, half, v);
+            }
             if (half == 1) {
               fence_proxy_async_smem();
               __syncwarp();
@@ -585,7 +630,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-template <typename InT, int BLOCK_N, int EPI, typename OutT, bool DUAL, int CTAS = 1>
+template <typename InT, int BLOCK_N, int EPI, typename OutT, bool DUAL, int CTAS = 1, bool QKN = false>
 int launch_tc(const LinearArgs& a, cudaStream_t stream) {
   using SM = GemmSmem<BLOCK_N, EPI, OutT, DUAL, CTAS>;
   constexpr int BLOCK_K = TILE_K_BYTES / (int)sizeof(InT);
@@ -640,7 +685,7 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
     tmK = tmO;
     tmV = tmO;
   }
-  auto kern = gemm_tcgen05_kernel<InT, BLOCK_N, EPI, OutT, DUAL, CTAS>;
+  auto kern = gemm_tcgen05_kernel<InT, BLOCK_N, EPI, OutT, DUAL, CTAS, QKN>;
   static bool attr_set = false;
   if (!attr_set) {
     GN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
@@ -684,6 +729,11 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
     t.dbg = e ? atoi(e) : 0;
   }
   t.a_hint = a.a_evict_first;
+  t.qkn_g = a.qkn_gamma; t.qkn_b = a.qkn_beta; t.qkn_cols = a.qkn_gamma ? a.qkn_cols : 0;
+  if ((t.qkn_cols > 0) != QKN || (QKN && !(SM::WIDE && EPI == EPI_STORE))) {
+    set_error("qk-LayerNorm epilogue needs the wide bf16 store epilogue (N %% 128 == 0)");
+    return GN_ERR_UNSUPPORTED;
+  }
   t.w_prefetch = env_on("GENIE_B200_W_PREFETCH", false) ? 1 : 0;   // measured: 257.9 vs 257.3 ms per step -> off
   if (kv) { t.kv_d = a.kv_d; t.kv_hd = a.kv_hd; t.kv_S = a.kv_S; t.kv_Tact = a.kv_Tact; t.kv_t0 = a.kv_t0; }
   if (a.conv) {
@@ -706,6 +756,9 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
 template <typename InT, int BLOCK_N, int CTAS = 1>
 int dispatch_epi(const LinearArgs& a, cudaStream_t s) {
   if (a.epi == EPI_STORE) {
+    if constexpr (sizeof(InT) == 2 && BLOCK_N >= 128) {
+      if (a.out_bf16 && a.qkn_gamma) return launch_tc<InT, BLOCK_N, EPI_STORE, bf16, false, CTAS, true>(a, s);
+    }
     return a.out_bf16 ? launch_tc<InT, BLOCK_N, EPI_STORE, bf16, false, CTAS>(a, s)
                       : launch_tc<InT, BLOCK_N, EPI_STORE, float, false, CTAS>(a, s);
   }
@@ -845,6 +898,12 @@ int linear_forward(const LinearArgs& a, cudaStream_t stream) {
                    a.kv_Tact > 0 && a.kv_t0 >= 0 && a.kv_t0 + a.kv_Tact <= a.kv_T && a.M == a.kv_clips * a.kv_Tact * a.kv_S,
                "K/V-cache output: inconsistent geometry");
   }
+  if (a.qkn_gamma) {
+    GN_REQUIRE(a.qkn_beta && a.epi == EPI_STORE && a.in_bf16 && a.out_bf16 && !a.force_simt && !a.conv &&
+                   a.qkn_cols > 0 && a.qkn_cols % (2 * EPI_COLS) == 0 && a.qkn_cols <= a.N && a.N % 128 == 0 &&
+                   !a.ln_stats,
+               "qk-LayerNorm epilogue: bf16 store epilogue on the tensor path, head_dim 64, N %% 128 == 0");
+  }
   const bool tc_ok = !a.force_simt && (a.N % 64 == 0) && (a.K * esz % 16 == 0) && (a.lda * esz % 16 == 0) &&
                      (a.ldw * esz % 16 == 0) && (a.ldo * (a.out_bf16 ? 2 : 4) % 16 == 0) &&
                      (!a.out2 || a.ldo2 * 2 % 16 == 0) && (!a.resid || a.ldr * 4 % 16 == 0) &&
@@ -856,6 +915,7 @@ int linear_forward(const LinearArgs& a, cudaStream_t stream) {
                      !(a.out2 && (a.epi != EPI_RESID || a.out_bf16));
   if (tc_ok) return a.in_bf16 ? dispatch_n<bf16>(a, stream) : dispatch_n<float>(a, stream);
   GN_REQUIRE(!a.kv_k, "K/V-cache output: operands not eligible for the tensor path");
+  GN_REQUIRE(!a.qkn_gamma, "qk-LayerNorm epilogue: operands not eligible for the tensor path");
   if (a.in_bf16)
     return a.out_bf16 ? launch_simt<bf16, bf16>(a, stream) : launch_simt<bf16, float>(a, stream);
   return a.out_bf16 ? launch_simt<float, bf16>(a, stream) : launch_simt<float, float>(a, stream);

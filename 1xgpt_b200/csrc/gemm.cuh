@@ -44,6 +44,12 @@ struct LinearArgs {
   int out_bf16;       // 1: out is bf16, 0: f32
   int force_simt;     // 1: CUDA-core fp32 path regardless of shape
   int round_out_tf32; // 1: round the fp32 output to tf32 (it feeds a kind::tf32 GEMM next)
+  // qk-LayerNorm (attention.py:42-47: LayerNorm(head_dim) with one shared affine on q and k) applied in the epilogue of
+  // the QKV projection: output columns [0, qkn_cols) are normalised per group of 64 (= one head) in fp32 before the
+  // bf16 rounding; bf16 tensor path with the store epilogue only (head_dim must be 64).  nullptr: off.
+  const float* qkn_gamma;
+  const float* qkn_beta;
+  int qkn_cols;
   int a_evict_first;  // 1: A is not read again after this GEMM (L2 evict_first hint on its loads)
   const ConvGeom* conv; // non-null: implicit-GEMM 3x3 convolution (A = NHWC input, K = 9*Cin, M = Nimg*Ho*Wo)
   // LayerNorm folded into the epilogue (A holds the RAW bf16 rows, W holds W*diag(gamma)):

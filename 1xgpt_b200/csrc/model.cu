@@ -61,6 +61,8 @@ struct gn_model {
   void* big = nullptr;    // [n, max(3d, hid)] act (qkv / mlp hidden)
   void* o = nullptr;      // [n, d] act
   float* stats = nullptr; // [n, d/64, 2] row-statistics partials for the folded LayerNorm
+  int qkn_epi = 0;        // qk-LayerNorm applied by the QKV GEMM epilogue (bf16, head_dim 64): the attention kernels then
+                          // see already-normalised q / k and the tcgen05 spatial + temporal v2 kernels apply
   int tv2 = 0;            // temporal attention v2: head-major K/V caches written by the temporal QKV GEMM epilogue
   void* scr_k = nullptr;  // [chunk clips * S][H][T][hd] scratch K/V for tv2 when the persistent cache is off
   void* scr_v = nullptr;
@@ -238,8 +240,11 @@ struct LnFold {
 
 int linear(gn_model* m, const void* A, int64_t lda, const void* W, int K, const float* bias, const float* resid,
            void* out, int64_t ldo, void* out2, int M, int N, int epi, int out_bf16, cudaStream_t st,
-           const LnFold* lf = nullptr, const KvOut* kv = nullptr) {
+           const LnFold* lf = nullptr, const KvOut* kv = nullptr, const AttnW* qkn = nullptr) {
   LinearArgs la{};
+  if (qkn && m->qkn_epi) {   // q and k columns [0, 2d) get LayerNorm(head_dim) with the attention's shared affine
+    la.qkn_gamma = qkn->norm_g; la.qkn_beta = qkn->norm_b; la.qkn_cols = 2 * m->cfg.d_model;
+  }
   if (kv && kv->k) {
     la.kv_k = kv->k; la.kv_v = kv->v; la.kv_d = m->cfg.d_model; la.kv_hd = m->cfg.d_model / m->cfg.num_heads;
     la.kv_T = m->cfg.T; la.kv_S = m->cfg.S; la.kv_Tact = kv->Tact; la.kv_t0 = kv->t0; la.kv_clips = kv->clips;
@@ -291,10 +296,11 @@ int temporal_block(gn_model* m, int l, const void* ain, AttnArgs aa, int b0, int
     KvOut kv;
     kv.k = kc; kv.v = vc; kv.t0 = t0; kv.Tact = Tact; kv.clips = nb;
     GN_PROPAGATE(linear(m, ain, d, w.qkv_w, d, w.qkv_b, nullptr, m->big, 3 * d, nullptr, n, 3 * d, EPI_STORE, 1, st,
-                        nullptr, &kv));
+                        nullptr, &kv, &w));
     GN_PROPAGATE(launch_temporal_attention_v2(aa, nb, S, T, t0, Tact, kc, vc, st));
   } else {
-    GN_PROPAGATE(linear(m, ain, d, w.qkv_w, d, w.qkv_b, nullptr, m->big, 3 * d, nullptr, n, 3 * d, EPI_STORE, bf, st));
+    GN_PROPAGATE(linear(m, ain, d, w.qkv_w, d, w.qkv_b, nullptr, m->big, 3 * d, nullptr, n, 3 * d, EPI_STORE, bf, st,
+                        nullptr, nullptr, &w));
     GN_PROPAGATE(launch_temporal_attention(aa, nb, S, T, t0, Tact, kc, vc, c.generic_attention || !bf, st));
   }
   m->flops_executed += 4.0 * (t0 + Tact) * (double)d * n;
@@ -419,10 +425,11 @@ int run_layers_body(gn_model* m, int b0, int nb, int t0, int Tact, bool use_cach
       ain = m->x;
     }
     GN_PROPAGATE(linear(m, ain, d, w.attn[0].qkv_w, d, w.attn[0].qkv_b, nullptr, m->big, 3 * d, nullptr, n, 3 * d,
-                        EPI_STORE, bf, st));
+                        EPI_STORE, bf, st, nullptr, nullptr, &w.attn[0]));
     AttnArgs aa{};
     aa.qkv = m->big; aa.out = m->o; aa.act_bf16 = bf; aa.n_heads = H; aa.head_dim = hd; aa.scale = scale;
-    aa.qk_gamma = w.attn[0].norm_g; aa.qk_beta = w.attn[0].norm_b; aa.round_tf32 = tf;
+    aa.round_tf32 = tf;
+    if (!m->qkn_epi) { aa.qk_gamma = w.attn[0].norm_g; aa.qk_beta = w.attn[0].norm_b; }
     GN_PROPAGATE(launch_spatial_attention(aa, nb * Tact, S, c.generic_attention || !bf, st));
     m->flops_executed += 4.0 * S * (double)d * n;
     // the temporal QKV GEMM reads the un-normalised stream: emit its bf16 copy from this epilogue
@@ -430,7 +437,7 @@ int run_layers_body(gn_model* m, int b0, int nb, int t0, int Tact, bool use_cach
                         EPI_RESID, 0, st));
     if (tf) GN_PROPAGATE(launch_prep(m->x, m->a, 0, nullptr, nullptr, n, d, 1.f, S, Tact, -1, st, 1));
     // ---------------- temporal attention (no LayerNorm in front: st_transformer.py:78)
-    aa.qk_gamma = w.attn[1].norm_g; aa.qk_beta = w.attn[1].norm_b;
+    if (!m->qkn_epi) { aa.qk_gamma = w.attn[1].norm_g; aa.qk_beta = w.attn[1].norm_b; }
     GN_PROPAGATE(temporal_block(m, l, cp ? m->a : (const void*)m->x, aa, b0, nb, t0, Tact, use_cache, st));
     const bool copy_t = bf && c.qk_norm;
     GN_PROPAGATE(linear(m, m->o, d, w.attn[1].proj_w, d, w.attn[1].proj_b, m->x, m->x, d, copy_t ? m->a : nullptr, n,
@@ -698,7 +705,12 @@ int gn_model_create(gn_model** out, const gn_config* cfg, int device) {
     const bool on = !(e && (e[0] == '0' || e[0] == 'n' || e[0] == 'N'));
     AttnArgs probe{};
     probe.act_bf16 = m->act_bf16; probe.n_heads = cfg->num_heads; probe.head_dim = cfg->d_model / cfg->num_heads;
-    m->tv2 = (on && !cfg->qk_norm && !cfg->generic_attention && temporal_v2_supported(probe, cfg->S, cfg->T)) ? 1 : 0;
+    const char* q = getenv("GENIE_B200_QKN_EPI");   // 0: keep qk-LayerNorm inside the (mma.sync) attention kernels
+    const bool qon = !(q && (q[0] == '0' || q[0] == 'n' || q[0] == 'N'));
+    m->qkn_epi = (qon && cfg->qk_norm && m->act_bf16 && !cfg->generic_attention && probe.head_dim == 64 &&
+                  (3 * cfg->d_model) % 128 == 0) ? 1 : 0;
+    m->tv2 = (on && (!cfg->qk_norm || m->qkn_epi) && !cfg->generic_attention &&
+              temporal_v2_supported(probe, cfg->S, cfg->T)) ? 1 : 0;
   }
   m->lanes = cfg->lanes <= 0 ? 1 : std::min<int>(cfg->lanes, gn_model::kMaxLanes);   // measured neutral on B200: off by default
   m->hid = (int)(cfg->d_model * cfg->mlp_ratio);

@@ -23,12 +23,13 @@ ap.add_argument("--maskgit-steps", type=int, default=8)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--dense", action="store_true")
+ap.add_argument("--qk-norm", action="store_true", help="qk_norm=True, use_mup=True (GenieConfig defaults of the reference)")
 a = ap.parse_args()
 
 dev = torch.device("cuda", 0)
 torch.cuda.set_stream(torch.cuda.Stream(dev))
 cfg = pkg.GenieConfig(num_layers=a.layers, num_heads=a.heads, d_model=a.d_model, T=16, S=256, image_vocab_size=262144,
-                      num_factored_vocabs=2, qk_norm=False, use_mup=False)
+                      num_factored_vocabs=2, qk_norm=a.qk_norm, use_mup=a.qk_norm)
 m = pkg.STMaskGIT(cfg, precision="bf16", kv_cache=not a.dense)
 m.load_state_dict(pkg.synthetic_state_dict(cfg, seed=0, bias_std=0.02))
 m = m.to(dev)
@@ -61,7 +62,7 @@ ms = e0.elapsed_time(e1) / a.steps
 frames = B * (T - TP)
 dense_flops = m.flops_per_clip_forward() * B * (T - TP) * K
 print(json.dumps({"workload": f"GENIE L{a.layers} d{a.d_model} h{a.heads} generate, {B} clips, MaskGIT-{K}, "
-                              f"{'dense' if a.dense else 'K/V-cached'}",
+                              f"{'dense' if a.dense else 'K/V-cached'}{', qk_norm+muP' if a.qk_norm else ''}",
                   "params_M": round(sum(p.numel() for p in m.parameters()) / 1e6, 1),
                   "ms_per_step": ms, "frames_per_s": frames / (ms / 1e3),
                   "executed_tflops": m.flops_executed() / a.steps / (ms / 1e3) / 1e12,
