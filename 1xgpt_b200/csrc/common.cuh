@@ -68,7 +68,7 @@ extern bool g_prof_on;
 // "persisting" property: the stream is read and rewritten by 3 residual GEMMs and read by 2 LayerNorm passes per block,
 // so keeping it in the L2 set-aside removes most of its HBM traffic (the wide activations - QKV, MLP hidden - stream
 // through the rest of L2).  num_bytes == 0: no attribute.
-extern cudaAccessPolicyWindow g_l2_window;
+extern thread_local cudaAccessPolicyWindow g_l2_window;   // per host thread: handles on different threads do not interfere
 inline int add_l2_window_attr(cudaLaunchAttribute* attr, int n) {
   if (g_l2_window.num_bytes == 0) return n;
   attr[n].id = cudaLaunchAttributeAccessPolicyWindow;

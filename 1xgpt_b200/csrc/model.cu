@@ -315,6 +315,7 @@ int run_layers_body(gn_model* m, int b0, int nb, int t0, int Tact, bool use_cach
 struct L2WindowScope {
   explicit L2WindowScope(const gn_model* m, int64_t n_rows) {
     static int64_t setaside = -1;   // bytes available for persisting lines (0: unsupported / disabled)
+    static int64_t max_window_bytes = 0;
     if (setaside < 0) {
       setaside = 0;
       // MB of L2 set aside for the residual stream (0 = off).  Measured on B200 (126 MB L2): 48 MB +1.7 % frames/s,
@@ -331,11 +332,14 @@ struct L2WindowScope {
         size_t got = 0;
         cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize);
         setaside = (int64_t)std::min<size_t>(got, (size_t)max_window);
+        max_window_bytes = max_window;
       }
       cudaGetLastError();
     }
     if (setaside <= 0 || m->x == nullptr) return;
-    const int64_t bytes = n_rows * m->cfg.d_model * 4;
+    // the window may not exceed cudaDevAttrMaxAccessPolicyWindowSize (128 MB on B200): larger chunks keep the policy
+    // on their first rows only (a launch with a larger window fails with cudaErrorInvalidValue)
+    const int64_t bytes = std::min<int64_t>(n_rows * m->cfg.d_model * 4, max_window_bytes);
     g_l2_window.base_ptr = m->x;
     g_l2_window.num_bytes = (size_t)bytes;
     g_l2_window.hitRatio = bytes <= setaside ? 1.0f : (float)setaside / (float)bytes;

@@ -19,7 +19,7 @@ bool g_use_pdl = env_flag("GENIE_B200_PDL", true);
 
 // ---- live launch profiler
 bool g_prof_on = false;
-cudaAccessPolicyWindow g_l2_window = {};
+thread_local cudaAccessPolicyWindow g_l2_window = {};
 namespace {
 struct Prof {
   std::vector<cudaEvent_t> ev;

@@ -405,3 +405,14 @@ def test_tiny_maskgit_categorical_sampling_matches_oracle(name):
     gen = m.generate(ids[:, :2].reshape(B, -1).cuda(), None, max_new_tokens=2 * cfg.S, maskgit_steps=2,
                      temperature=1.0, noise=gn, uniform=gu)
     assert torch.equal(gen.cpu(), full.reshape(B, -1))
+
+
+def test_chunk_larger_than_l2_policy_window():
+    """A chunk whose fp32 residual stream (rows x d x 4 B) exceeds cudaDevAttrMaxAccessPolicyWindowSize (128 MB) must
+    run (the persisting-L2 window is clamped) and give the same logits as the default chunking, bit for bit."""
+    z, kw, cfg, sd = _prod_setup("genie138m")
+    ids = torch.from_numpy(z["ids"]).long()
+    ids = torch.cat([ids.roll(i, 2) for i in range(9)], 0)            # 18 clips = 73728 rows: x = 151 MB in one chunk
+    a = build_b200_model(kw, sd, precision="bf16", chunk_tokens=131072).compute_logits(ids.cuda())
+    b = build_b200_model(kw, sd, precision="bf16").compute_logits(ids.cuda())
+    assert torch.equal(a.cpu(), b.cpu())
