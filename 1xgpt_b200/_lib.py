@@ -8,9 +8,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgenie_b200.so")
 
-GN_PREC_BF16, GN_PREC_TF32, GN_PREC_FP32 = 0, 1, 2
+GN_PREC_BF16, GN_PREC_TF32, GN_PREC_FP32, GN_PREC_FP16 = 0, 1, 2, 3
 GN_UNMASK_RANDOM, GN_UNMASK_GREEDY = 0, 1
-PRECISIONS = {"bf16": GN_PREC_BF16, "tf32": GN_PREC_TF32, "fp32": GN_PREC_FP32}
+PRECISIONS = {"bf16": GN_PREC_BF16, "tf32": GN_PREC_TF32, "fp32": GN_PREC_FP32, "fp16": GN_PREC_FP16}
 
 
 class GnError(RuntimeError):
@@ -67,6 +67,7 @@ SIGNATURES = {
     "gn_profile_begin": (_i, []),
     "gn_profile_end": (_i, [C.POINTER(C.c_double)]),
     "gn_kernel_launches": (C.c_uint64, []),
+    "gn_fallback_launches": (C.c_uint64, []),
     "gn_model_flops_per_clip_forward": (C.c_double, [_vp]),
     "gn_model_flops_executed": (C.c_double, [_vp]),
     "gn_model_reset_counters": (None, [_vp]),

@@ -13,11 +13,19 @@
 namespace gn {
 namespace {
 
+template <typename H>
 __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  if constexpr (sizeof(H) == 2 && H16<H>::UMMA_FMT == 1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  } else {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
 }
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -39,7 +47,7 @@ __device__ __forceinline__ uint32_t swz(int r, int c) {
 }
 
 // In-place LayerNorm(head_dim) of `nrows` staged rows (shared affine, eps 1e-5), CH = HD/8 lanes per row.
-template <int HD>
+template <int HD, typename H>
 __device__ __forceinline__ void qk_layernorm_rows(uint8_t* tile, int nrows, int tid, int nthreads,
                                                   const float* __restrict__ gamma, const float* __restrict__ beta) {
   constexpr int CH = HD / 8;
@@ -50,11 +58,11 @@ __device__ __forceinline__ void qk_layernorm_rows(uint8_t* tile, int nrows, int 
     const bool act = r < nrows;
     uint4* p = reinterpret_cast<uint4*>(tile + swz<HD>(act ? r : 0, sub));
     uint4 raw = act ? *p : make_uint4(0, 0, 0, 0);
-    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    const uint32_t* h2 = reinterpret_cast<const uint32_t*>(&raw);
     float v[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float2 f = __bfloat1622float2(h2[i]);
+      const float2 f = unpack_h2<H>(h2[i]);
       v[2 * i] = f.x;
       v[2 * i + 1] = f.y;
     }
@@ -75,7 +83,7 @@ __device__ __forceinline__ void qk_layernorm_rows(uint8_t* tile, int nrows, int 
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int c0 = sub * 8 + 2 * i;
-      ow[i] = pack_bf16x2((v[2 * i] - mean) * rstd * gamma[c0] + beta[c0],
+      ow[i] = pack_h2<H>((v[2 * i] - mean) * rstd * gamma[c0] + beta[c0],
                           (v[2 * i + 1] - mean) * rstd * gamma[c0 + 1] + beta[c0 + 1]);
     }
     if (act) *p = outv;
@@ -88,10 +96,10 @@ __device__ __forceinline__ void qk_layernorm_rows(uint8_t* tile, int nrows, int 
 constexpr int SP_THREADS = 256;
 constexpr int SP_QROWS = 128;
 
-template <int HD>
+template <int HD, typename H>
 __global__ void __launch_bounds__(SP_THREADS, 2)
 spatial_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                    bf16* __restrict__ out, int S, int d, float scale_log2e, const float* __restrict__ gamma,
+                    H* __restrict__ out, int S, int d, float scale_log2e, const float* __restrict__ gamma,
                     const float* __restrict__ beta) {
   constexpr int ROWB = HD * 2;  // bytes per staged row
   constexpr int CH = HD / 8;    // 16-byte chunks per row
@@ -124,8 +132,8 @@ spatial_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
   mbar_wait(&bars[0], 0);
   if (gamma != nullptr) {
-    qk_layernorm_rows<HD>(sQ, SP_QROWS, tid, SP_THREADS, gamma, beta);
-    qk_layernorm_rows<HD>(sK, S, tid, SP_THREADS, gamma, beta);
+    qk_layernorm_rows<HD, H>(sQ, SP_QROWS, tid, SP_THREADS, gamma, beta);
+    qk_layernorm_rows<HD, H>(sK, S, tid, SP_THREADS, gamma, beta);
     __syncthreads();
   }
 
@@ -154,8 +162,8 @@ spatial_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int jp = 0; jp < 4; ++jp) {
         uint32_t b[4];
         ldsm_x4(b, sKa + swz<HD>(kb * 64 + (2 * jp + (mi >> 1)) * 8 + l8, 2 * kk + (mi & 1)));
-        mma_16816(s[2 * jp], qf[kk], b[0], b[1]);
-        mma_16816(s[2 * jp + 1], qf[kk], b[2], b[3]);
+        mma_16816<H>(s[2 * jp], qf[kk], b[0], b[1]);
+        mma_16816<H>(s[2 * jp + 1], qf[kk], b[2], b[3]);
       }
     }
     float mx0 = -INFINITY, mx1 = -INFINITY;
@@ -190,16 +198,16 @@ spatial_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
     for (int k2 = 0; k2 < 4; ++k2) {
       uint32_t a[4];
-      a[0] = pack_bf16x2(s[2 * k2][0], s[2 * k2][1]);
-      a[1] = pack_bf16x2(s[2 * k2][2], s[2 * k2][3]);
-      a[2] = pack_bf16x2(s[2 * k2 + 1][0], s[2 * k2 + 1][1]);
-      a[3] = pack_bf16x2(s[2 * k2 + 1][2], s[2 * k2 + 1][3]);
+      a[0] = pack_h2<H>(s[2 * k2][0], s[2 * k2][1]);
+      a[1] = pack_h2<H>(s[2 * k2][2], s[2 * k2][3]);
+      a[2] = pack_h2<H>(s[2 * k2 + 1][0], s[2 * k2 + 1][1]);
+      a[3] = pack_h2<H>(s[2 * k2 + 1][2], s[2 * k2 + 1][3]);
 #pragma unroll
       for (int jp = 0; jp < HD / 16; ++jp) {
         uint32_t b[4];
         ldsm_x4_t(b, sVa + swz<HD>(kb * 64 + k2 * 16 + (mi & 1) * 8 + l8, 2 * jp + (mi >> 1)));
-        mma_16816(o[2 * jp], a, b[0], b[1]);
-        mma_16816(o[2 * jp + 1], a, b[2], b[3]);
+        mma_16816<H>(o[2 * jp], a, b[0], b[1]);
+        mma_16816<H>(o[2 * jp + 1], a, b[2], b[3]);
       }
     }
   }
@@ -213,8 +221,8 @@ spatial_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < HD / 8; ++j) {
-    *reinterpret_cast<uint32_t*>(sQ + swz<HD>(warp * 16 + g, j) + t4 * 4) = pack_bf16x2(o[j][0] * i0, o[j][1] * i0);
-    *reinterpret_cast<uint32_t*>(sQ + swz<HD>(warp * 16 + g + 8, j) + t4 * 4) = pack_bf16x2(o[j][2] * i1, o[j][3] * i1);
+    *reinterpret_cast<uint32_t*>(sQ + swz<HD>(warp * 16 + g, j) + t4 * 4) = pack_h2<H>(o[j][0] * i0, o[j][1] * i0);
+    *reinterpret_cast<uint32_t*>(sQ + swz<HD>(warp * 16 + g + 8, j) + t4 * 4) = pack_h2<H>(o[j][2] * i1, o[j][3] * i1);
   }
   __syncwarp();
 #pragma unroll
@@ -226,23 +234,23 @@ spatial_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
-template <int HD>
+template <int HD, typename H>
 int launch_spatial_t(const AttnArgs& a, int n_frames, int S, cudaStream_t st) {
   const int d = a.n_heads * a.head_dim;
   const int64_t rows = (int64_t)n_frames * S;
   CUtensorMap tmQ, tmKV;
   const CUtensorMapSwizzle sw = HD == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  GN_PROPAGATE(make_tensor_map_2d(&tmQ, a.qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * d, rows, 3 * d, HD, SP_QROWS, sw));
-  GN_PROPAGATE(make_tensor_map_2d(&tmKV, a.qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * d, rows, 3 * d, HD, S, sw));
+  GN_PROPAGATE(make_tensor_map_2d(&tmQ, a.qkv, H16<H>::TMAP, 2, 3 * d, rows, 3 * d, HD, SP_QROWS, sw));
+  GN_PROPAGATE(make_tensor_map_2d(&tmKV, a.qkv, H16<H>::TMAP, 2, 3 * d, rows, 3 * d, HD, S, sw));
   const int smem = (SP_QROWS + 2 * S) * HD * 2 + 64 + 1024;
-  auto kern = spatial_attn_kernel<HD>;
+  auto kern = spatial_attn_kernel<HD, H>;
   static int set = 0;
   if (smem > set) {
     GN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     set = smem;
   }
   dim3 grid(S / SP_QROWS, a.n_heads, n_frames);
-  GN_CUDA_CHECK(launch_kernel(PC_SPATIAL, kern, grid, dim3(SP_THREADS), (size_t)smem, st, tmQ, tmKV, static_cast<bf16*>(a.out), S, d,
+  GN_CUDA_CHECK(launch_kernel(PC_SPATIAL, kern, grid, dim3(SP_THREADS), (size_t)smem, st, tmQ, tmKV, static_cast<H*>(a.out), S, d,
                               a.scale * 1.4426950408889634f, a.qk_gamma, a.qk_beta));
   ++g_launch_count;
   return GN_OK;
@@ -262,10 +270,10 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int HD>
+template <int HD, typename H>
 __global__ void __launch_bounds__(512)
-temporal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, bf16* __restrict__ kcache,
-                     bf16* __restrict__ vcache, int n_pos, int S, int T, int t0, int Tq, int d, float scale_log2e,
+temporal_attn_kernel(const H* __restrict__ qkv, H* __restrict__ out, H* __restrict__ kcache,
+                     H* __restrict__ vcache, int n_pos, int S, int T, int t0, int Tq, int d, float scale_log2e,
                      const float* __restrict__ gamma, const float* __restrict__ beta) {
   constexpr int ROWB = HD * 2;
   constexpr int CH = HD / 8;
@@ -293,9 +301,9 @@ temporal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, bf16*
     for (int it = 0; it < NIT; ++it) {
       const int idx = it * 32 + lane;
       const int r = idx / CH, c = idx % CH;
-      const bf16* qsrc = qkv + (fresh0 + (int64_t)(r < Tq ? r : 0) * S) * 3 * d + h * HD + c * 8;
+      const H* qsrc = qkv + (fresh0 + (int64_t)(r < Tq ? r : 0) * S) * 3 * d + h * HD + c * 8;
       cp_async16(sQ + swz<HD>(r, c), qsrc, r < Tq);
-      const bf16 *ksrc, *vsrc;
+      const H *ksrc, *vsrc;
       if (r < t0) {
         const int64_t cr = (cache0 + r) * d + h * HD + c * 8;
         ksrc = kcache + cr;
@@ -343,8 +351,8 @@ temporal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, bf16*
       }
     }
     if (gamma != nullptr) {
-      qk_layernorm_rows<HD>(sQ, Tq, lane, 32, gamma, beta);
-      qk_layernorm_rows<HD>(sK, Tk, lane, 32, gamma, beta);
+      qk_layernorm_rows<HD, H>(sQ, Tq, lane, 32, gamma, beta);
+      qk_layernorm_rows<HD, H>(sK, Tk, lane, 32, gamma, beta);
       __syncwarp();
     }
     const uint32_t sQa = smem_u32(sQ), sKa = smem_u32(sK), sVa = smem_u32(sV);
@@ -357,8 +365,8 @@ temporal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, bf16*
       uint32_t qf[4], kf[4];
       ldsm_x4(qf, sQa + swz<HD>(l8 + (mi & 1) * 8, 2 * kk + (mi >> 1)));
       ldsm_x4(kf, sKa + swz<HD>((mi >> 1) * 8 + l8, 2 * kk + (mi & 1)));
-      mma_16816(s[0], qf, kf[0], kf[1]);
-      mma_16816(s[1], qf, kf[2], kf[3]);
+      mma_16816<H>(s[0], qf, kf[0], kf[1]);
+      mma_16816<H>(s[1], qf, kf[2], kf[3]);
     }
     // causal mask: query row i (frame t0 + i) sees keys j <= t0 + i   (attention.py:51-55)
     float mx0 = -INFINITY, mx1 = -INFINITY;
@@ -394,10 +402,10 @@ temporal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, bf16*
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float i0 = 1.f / l0, i1 = 1.f / l1;
     uint32_t pa[4];
-    pa[0] = pack_bf16x2(s[0][0], s[0][1]);
-    pa[1] = pack_bf16x2(s[0][2], s[0][3]);
-    pa[2] = pack_bf16x2(s[1][0], s[1][1]);
-    pa[3] = pack_bf16x2(s[1][2], s[1][3]);
+    pa[0] = pack_h2<H>(s[0][0], s[0][1]);
+    pa[1] = pack_h2<H>(s[0][2], s[0][3]);
+    pa[2] = pack_h2<H>(s[1][0], s[1][1]);
+    pa[3] = pack_h2<H>(s[1][2], s[1][3]);
     float o[HD / 8][4];
 #pragma unroll
     for (int jp = 0; jp < HD / 16; ++jp) {
@@ -405,14 +413,14 @@ temporal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, bf16*
       ldsm_x4_t(vf, sVa + swz<HD>((mi & 1) * 8 + l8, 2 * jp + (mi >> 1)));
       o[2 * jp][0] = o[2 * jp][1] = o[2 * jp][2] = o[2 * jp][3] = 0.f;
       o[2 * jp + 1][0] = o[2 * jp + 1][1] = o[2 * jp + 1][2] = o[2 * jp + 1][3] = 0.f;
-      mma_16816(o[2 * jp], pa, vf[0], vf[1]);
-      mma_16816(o[2 * jp + 1], pa, vf[2], vf[3]);
+      mma_16816<H>(o[2 * jp], pa, vf[0], vf[1]);
+      mma_16816<H>(o[2 * jp + 1], pa, vf[2], vf[3]);
     }
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < HD / 8; ++j) {
-      *reinterpret_cast<uint32_t*>(sQ + swz<HD>(g, j) + t4 * 4) = pack_bf16x2(o[j][0] * i0, o[j][1] * i0);
-      *reinterpret_cast<uint32_t*>(sQ + swz<HD>(g + 8, j) + t4 * 4) = pack_bf16x2(o[j][2] * i1, o[j][3] * i1);
+      *reinterpret_cast<uint32_t*>(sQ + swz<HD>(g, j) + t4 * 4) = pack_h2<H>(o[j][0] * i0, o[j][1] * i0);
+      *reinterpret_cast<uint32_t*>(sQ + swz<HD>(g + 8, j) + t4 * 4) = pack_h2<H>(o[j][2] * i1, o[j][3] * i1);
     }
     __syncwarp();
 #pragma unroll
@@ -428,12 +436,12 @@ temporal_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, bf16*
   }
 }
 
-template <int HD>
+template <int HD, typename H>
 int launch_temporal_t(const AttnArgs& a, int B, int S, int T, int t0, int Tq, void* kcache, void* vcache,
                       cudaStream_t st) {
   const int d = a.n_heads * a.head_dim;
   const int smem = a.n_heads * 2 * 3 * 16 * HD * 2 + 1024;
-  auto kern = temporal_attn_kernel<HD>;
+  auto kern = temporal_attn_kernel<HD, H>;
   static int set = 0;
   if (smem > 48 * 1024 && smem > set) {
     GN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -450,8 +458,8 @@ int launch_temporal_t(const AttnArgs& a, int B, int S, int T, int t0, int Tq, vo
   const int n_pos = B * S;
   const int grid = std::min(n_pos, sms * per_sm);
   GN_CUDA_CHECK(launch_kernel(PC_TEMPORAL, kern, dim3(grid), dim3(a.n_heads * 32), (size_t)smem, st,
-                              static_cast<const bf16*>(a.qkv), static_cast<bf16*>(a.out), static_cast<bf16*>(kcache),
-                              static_cast<bf16*>(vcache), n_pos, S, T, t0, Tq, d, a.scale * 1.4426950408889634f,
+                              static_cast<const H*>(a.qkv), static_cast<H*>(a.out), static_cast<H*>(kcache),
+                              static_cast<H*>(vcache), n_pos, S, T, t0, Tq, d, a.scale * 1.4426950408889634f,
                               a.qk_gamma, a.qk_beta));
   ++g_launch_count;
   return GN_OK;
@@ -472,6 +480,7 @@ __device__ __forceinline__ uint32_t line_off(int line, int c) {      // SWIZZLE_
   return (uint32_t)(line * 128 + ((c ^ (line & 7)) << 4));
 }
 
+template <typename E>
 __global__ void __launch_bounds__(576, 1)
 temporal_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, int n_pos,
@@ -568,8 +577,8 @@ temporal_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         uint32_t qf[4], kf[4];
         ldsm_x4(qf, sQa + qo[kk]);
         ldsm_x4(kf, sKa + ko[kk]);
-        mma_16816(s[0], qf, kf[0], kf[1]);
-        mma_16816(s[1], qf, kf[2], kf[3]);
+        mma_16816<E>(s[0], qf, kf[0], kf[1]);
+        mma_16816<E>(s[1], qf, kf[2], kf[3]);
       }
       // causal mask: query row i (frame t0 + i) sees keys j <= t0 + i   (attention.py:51-55)
       float mx0 = -INFINITY, mx1 = -INFINITY;
@@ -605,10 +614,10 @@ temporal_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
       const float i0 = 1.f / l0, i1 = 1.f / l1;
       uint32_t pa[4];
-      pa[0] = pack_bf16x2(s[0][0], s[0][1]);
-      pa[1] = pack_bf16x2(s[0][2], s[0][3]);
-      pa[2] = pack_bf16x2(s[1][0], s[1][1]);
-      pa[3] = pack_bf16x2(s[1][2], s[1][3]);
+      pa[0] = pack_h2<E>(s[0][0], s[0][1]);
+      pa[1] = pack_h2<E>(s[0][2], s[0][3]);
+      pa[2] = pack_h2<E>(s[1][0], s[1][1]);
+      pa[3] = pack_h2<E>(s[1][2], s[1][3]);
       float o[HD / 8][4];
 #pragma unroll
       for (int jp = 0; jp < HD / 16; ++jp) {
@@ -616,20 +625,20 @@ temporal_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         ldsm_x4_t(vf, sVa + vo[jp]);
         o[2 * jp][0] = o[2 * jp][1] = o[2 * jp][2] = o[2 * jp][3] = 0.f;
         o[2 * jp + 1][0] = o[2 * jp + 1][1] = o[2 * jp + 1][2] = o[2 * jp + 1][3] = 0.f;
-        mma_16816(o[2 * jp], pa, vf[0], vf[1]);
-        mma_16816(o[2 * jp + 1], pa, vf[2], vf[3]);
+        mma_16816<E>(o[2 * jp], pa, vf[0], vf[1]);
+        mma_16816<E>(o[2 * jp + 1], pa, vf[2], vf[3]);
       }
       __syncwarp();        // every lane's Q fragments are in registers: the Q lines of this head become output staging
       if (g < Tq) {
 #pragma unroll
         for (int c = 0; c < HD / 8; ++c)
-          *reinterpret_cast<uint32_t*>(base + line_off(g * H + h, c) + t4 * 4) = pack_bf16x2(o[c][0] * i0, o[c][1] * i0);
+          *reinterpret_cast<uint32_t*>(base + line_off(g * H + h, c) + t4 * 4) = pack_h2<E>(o[c][0] * i0, o[c][1] * i0);
       }
       if (g + 8 < Tq) {
 #pragma unroll
         for (int c = 0; c < HD / 8; ++c)
           *reinterpret_cast<uint32_t*>(base + line_off((g + 8) * H + h, c) + t4 * 4) =
-              pack_bf16x2(o[c][2] * i1, o[c][3] * i1);
+              pack_h2<E>(o[c][2] * i1, o[c][3] * i1);
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -639,6 +648,7 @@ temporal_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   }
 }
 
+template <typename E>
 int launch_temporal_v2(const AttnArgs& a, int nb, int S, int T, int t0, int Tq, const void* kc, const void* vc,
                        cudaStream_t st) {
   const int H = a.n_heads, HD = 64, d = H * HD, Tk = t0 + Tq;
@@ -649,15 +659,15 @@ int launch_temporal_v2(const AttnArgs& a, int nb, int S, int T, int t0, int Tq, 
     const int64_t sq[3] = {HD * 2, (int64_t)3 * d * 2, (int64_t)S * 3 * d * 2};
     const int64_t so[3] = {HD * 2, (int64_t)d * 2, (int64_t)S * d * 2};
     const int box[4] = {HD, H, 1, Tq};
-    GN_PROPAGATE(make_tensor_map_nd(&tmQ, a.qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, sq, box,
+    GN_PROPAGATE(make_tensor_map_nd(&tmQ, a.qkv, H16<E>::TMAP, 4, dims, sq, box,
                                     CU_TENSOR_MAP_SWIZZLE_128B));
-    GN_PROPAGATE(make_tensor_map_nd(&tmO, a.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, so, box,
+    GN_PROPAGATE(make_tensor_map_nd(&tmO, a.out, H16<E>::TMAP, 4, dims, so, box,
                                     CU_TENSOR_MAP_SWIZZLE_128B));
     const int64_t dk[3] = {HD, T, (int64_t)H * n_pos};
     const int64_t sk[2] = {HD * 2, (int64_t)T * HD * 2};
     const int bk[3] = {HD, Tk, H};
-    GN_PROPAGATE(make_tensor_map_nd(&tmK, kc, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dk, sk, bk, CU_TENSOR_MAP_SWIZZLE_128B));
-    GN_PROPAGATE(make_tensor_map_nd(&tmV, vc, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dk, sk, bk, CU_TENSOR_MAP_SWIZZLE_128B));
+    GN_PROPAGATE(make_tensor_map_nd(&tmK, kc, H16<E>::TMAP, 3, dk, sk, bk, CU_TENSOR_MAP_SWIZZLE_128B));
+    GN_PROPAGATE(make_tensor_map_nd(&tmV, vc, H16<E>::TMAP, 3, dk, sk, bk, CU_TENSOR_MAP_SWIZZLE_128B));
   }
   const int rq = (Tq * H * HD * 2 + 1023) & ~1023, rk = (Tk * H * HD * 2 + 1023) & ~1023;
   const int stage = rq + 2 * rk;
@@ -669,7 +679,7 @@ int launch_temporal_v2(const AttnArgs& a, int nb, int S, int T, int t0, int Tq, 
   if (ns > 8) ns = 8;
   GN_REQUIRE(ns >= 2, "temporal attention v2: a stage of %d bytes does not fit twice in shared memory", stage);
   const int smem = ns * stage + 1024 + 2 * ns * 8;
-  auto kern = temporal_attn_v2_kernel;
+  auto kern = temporal_attn_v2_kernel<E>;
   static bool attr_set = false;
   if (!attr_set) {
     GN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -696,15 +706,20 @@ bool fast_spatial_supported(const AttnArgs& a, int S) {
   return a.act_bf16 && (a.head_dim == 64 || a.head_dim == 32) && (S == 128 || S == 256);
 }
 int fast_spatial_attention(const AttnArgs& a, int n_frames, int S, cudaStream_t st) {
-  return a.head_dim == 64 ? launch_spatial_t<64>(a, n_frames, S, st) : launch_spatial_t<32>(a, n_frames, S, st);
+  if (a.fp16)
+    return a.head_dim == 64 ? launch_spatial_t<64, f16>(a, n_frames, S, st) : launch_spatial_t<32, f16>(a, n_frames, S, st);
+  return a.head_dim == 64 ? launch_spatial_t<64, bf16>(a, n_frames, S, st) : launch_spatial_t<32, bf16>(a, n_frames, S, st);
 }
 bool fast_temporal_supported(const AttnArgs& a, int T) {
   return a.act_bf16 && (a.head_dim == 64 || a.head_dim == 32) && T <= 16 && a.n_heads <= 16;
 }
 int fast_temporal_attention(const AttnArgs& a, int B, int S, int T, int t0, int Tq, void* kcache, void* vcache,
                             cudaStream_t st) {
-  return a.head_dim == 64 ? launch_temporal_t<64>(a, B, S, T, t0, Tq, kcache, vcache, st)
-                          : launch_temporal_t<32>(a, B, S, T, t0, Tq, kcache, vcache, st);
+  if (a.fp16)
+    return a.head_dim == 64 ? launch_temporal_t<64, f16>(a, B, S, T, t0, Tq, kcache, vcache, st)
+                            : launch_temporal_t<32, f16>(a, B, S, T, t0, Tq, kcache, vcache, st);
+  return a.head_dim == 64 ? launch_temporal_t<64, bf16>(a, B, S, T, t0, Tq, kcache, vcache, st)
+                          : launch_temporal_t<32, bf16>(a, B, S, T, t0, Tq, kcache, vcache, st);
 }
 
 int generic_temporal_attention(const AttnArgs& a, int B, int S, int T, int t0, int Tq, void* kcache, void* vcache,
@@ -718,11 +733,13 @@ int launch_temporal_attention_v2(const AttnArgs& a, int nb, int S, int T, int t0
   GN_REQUIRE(temporal_v2_supported(a, S, T), "temporal attention v2: unsupported shape");
   GN_REQUIRE(t0 >= 0 && Tq >= 1 && t0 + Tq <= T, "temporal attention: bad frame range t0=%d Tq=%d T=%d", t0, Tq, T);
   GN_REQUIRE(kcache && vcache, "temporal attention v2 reads K/V from the head-major caches");
-  return launch_temporal_v2(a, nb, S, T, t0, Tq, kcache, vcache, st);
+  return a.fp16 ? launch_temporal_v2<f16>(a, nb, S, T, t0, Tq, kcache, vcache, st)
+                : launch_temporal_v2<bf16>(a, nb, S, T, t0, Tq, kcache, vcache, st);
 }
 
 int launch_spatial_attention(const AttnArgs& a, int n_frames, int S, int force_generic, cudaStream_t st) {
   if (!force_generic && tc_spatial_supported(a, S)) return tc_spatial_attention(a, n_frames, S, st);
+  if (!force_generic) ++g_fallback_launches;   // a 16-bit handle left the tcgen05 kernel (head_dim != 64, qk-LN in kernel, S)
   if (!force_generic && fast_spatial_supported(a, S)) return fast_spatial_attention(a, n_frames, S, st);
   return launch_generic_attention(a, n_frames, S, 0, st);
 }
@@ -730,6 +747,7 @@ int launch_temporal_attention(const AttnArgs& a, int B, int S, int T, int t0, in
                               int force_generic, cudaStream_t st) {
   GN_REQUIRE(t0 >= 0 && Tq >= 1 && t0 + Tq <= T, "temporal attention: bad frame range t0=%d Tq=%d T=%d", t0, Tq, T);
   GN_REQUIRE(t0 == 0 || (kcache && vcache), "temporal attention with t0 > 0 needs the K/V caches");
+  if (!force_generic) ++g_fallback_launches;   // a 16-bit handle is not on the TMA-fed v2 kernel
   if (!force_generic && fast_temporal_supported(a, T))
     return fast_temporal_attention(a, B, S, T, t0, Tq, kcache, vcache, st);
   return generic_temporal_attention(a, B, S, T, t0, Tq, kcache, vcache, st);

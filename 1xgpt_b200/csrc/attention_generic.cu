@@ -168,6 +168,8 @@ int launch_generic_t(const AttnArgs& a, int n_seq, GenericMap mp, int nq, int nk
 
 int launch_generic_attention(const AttnArgs& a, int n_seq, int n_tok, int causal, cudaStream_t st) {
   GenericMap mp{1, n_tok, 1, 0, 0, 0};
+  if (a.act_bf16 && a.fp16)
+    return launch_generic_t<f16>(a, n_seq, mp, n_tok, 0, causal, nullptr, nullptr, nullptr, nullptr, st);
   return a.act_bf16 ? launch_generic_t<bf16>(a, n_seq, mp, n_tok, 0, causal, nullptr, nullptr, nullptr, nullptr, st)
                     : launch_generic_t<float>(a, n_seq, mp, n_tok, 0, causal, nullptr, nullptr, nullptr, nullptr, st);
 }
@@ -176,6 +178,7 @@ int generic_temporal_attention(const AttnArgs& a, int B, int S, int T, int t0, i
                                cudaStream_t st) {
   GenericMap mp{S, (int64_t)Tq * S, S, (int64_t)S * T, T, 1};   // cache layout [B, S, T, d]
   GN_REQUIRE(t0 == 0 || (kcache && vcache), "temporal attention with t0 > 0 needs the K/V caches");
+  if (a.act_bf16 && a.fp16) return launch_generic_t<f16>(a, B * S, mp, Tq, t0, 1, kcache, vcache, kcache, vcache, st);
   return a.act_bf16 ? launch_generic_t<bf16>(a, B * S, mp, Tq, t0, 1, kcache, vcache, kcache, vcache, st)
                     : launch_generic_t<float>(a, B * S, mp, Tq, t0, 1, kcache, vcache, kcache, vcache, st);
 }

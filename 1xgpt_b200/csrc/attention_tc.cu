@@ -52,13 +52,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int SK>
+template <int SK, typename H>
 __global__ void __launch_bounds__(TCA_THREADS, 2)
 spatial_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                        const __grid_constant__ CUtensorMap tmO, int d, float scale_log2e) {
   static_assert(SK == 128 || SK == 256, "keys per frame");
-  constexpr uint32_t IDESC_QK = umma_idesc(UMMA_FMT_BF16, TCA_QROWS, SK, 0, 0);
-  constexpr uint32_t IDESC_PV = umma_idesc(UMMA_FMT_BF16, TCA_QROWS, TCA_HD, 0, 1);
+  constexpr uint32_t IDESC_QK = umma_idesc(H16<H>::UMMA_FMT, TCA_QROWS, SK, 0, 0);
+  constexpr uint32_t IDESC_PV = umma_idesc(H16<H>::UMMA_FMT, TCA_QROWS, TCA_HD, 0, 1);
   constexpr int GC = SK / 2;      // score columns per thread: two threads (column groups) share a query row
   // group g keeps its packed P in columns [g*GC, g*GC + GC/2).  O takes 64 columns that hold no P: the consumed second
   // half of group 0's scores when that is wide enough (S = 256), else columns past the scores (S = 128)
@@ -162,8 +162,8 @@ spatial_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         const float p2 = ex2_approx(fmaf(__uint_as_float(r0[2 * i + 2]), scale_log2e, -off));
         const float p3 = ex2_approx(fmaf(__uint_as_float(r0[2 * i + 3]), scale_log2e, -off));
         l0 += p0; l1 += p1; l2 += p2; l3 += p3;
-        pk[i] = pack_bf16x2(p0, p1);
-        pk[i + 1] = pack_bf16x2(p2, p3);
+        pk[i] = pack_h2<H>(p0, p1);
+        pk[i + 1] = pack_h2<H>(p2, p3);
       }
       // packed P columns [16c, 16c+16) of this group lie inside its own, already consumed, score columns
       tmem_st_32x32b_x16(my_addr + c * 16, pk);
@@ -175,8 +175,8 @@ spatial_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         const float p2 = ex2_approx(fmaf(__uint_as_float(r1[2 * i + 2]), scale_log2e, -off));
         const float p3 = ex2_approx(fmaf(__uint_as_float(r1[2 * i + 3]), scale_log2e, -off));
         l0 += p0; l1 += p1; l2 += p2; l3 += p3;
-        pk[i] = pack_bf16x2(p0, p1);
-        pk[i + 1] = pack_bf16x2(p2, p3);
+        pk[i] = pack_h2<H>(p0, p1);
+        pk[i + 1] = pack_h2<H>(p2, p3);
       }
       tmem_st_32x32b_x16(my_addr + (c + 1) * 16, pk);
     }
@@ -212,10 +212,10 @@ spatial_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       uint4 v;
-      v.x = pack_bf16x2(__uint_as_float(r0[8 * c + 0]) * inv, __uint_as_float(r0[8 * c + 1]) * inv);
-      v.y = pack_bf16x2(__uint_as_float(r0[8 * c + 2]) * inv, __uint_as_float(r0[8 * c + 3]) * inv);
-      v.z = pack_bf16x2(__uint_as_float(r0[8 * c + 4]) * inv, __uint_as_float(r0[8 * c + 5]) * inv);
-      v.w = pack_bf16x2(__uint_as_float(r0[8 * c + 6]) * inv, __uint_as_float(r0[8 * c + 7]) * inv);
+      v.x = pack_h2<H>(__uint_as_float(r0[8 * c + 0]) * inv, __uint_as_float(r0[8 * c + 1]) * inv);
+      v.y = pack_h2<H>(__uint_as_float(r0[8 * c + 2]) * inv, __uint_as_float(r0[8 * c + 3]) * inv);
+      v.z = pack_h2<H>(__uint_as_float(r0[8 * c + 4]) * inv, __uint_as_float(r0[8 * c + 5]) * inv);
+      v.w = pack_h2<H>(__uint_as_float(r0[8 * c + 6]) * inv, __uint_as_float(r0[8 * c + 7]) * inv);
       *reinterpret_cast<uint4*>(srow + (((grp * 4 + c) ^ (row & 7)) << 4)) = v;
     }
   }
@@ -234,18 +234,18 @@ spatial_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   }
 }
 
-template <int SK>
+template <int SK, typename H>
 int launch_tc_t(const AttnArgs& a, int n_frames, cudaStream_t st) {
   const int d = a.n_heads * a.head_dim;
   const int64_t rows = (int64_t)n_frames * SK;
   CUtensorMap tmQ, tmKV, tmO;
   const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
-  GN_PROPAGATE(make_tensor_map_2d(&tmQ, a.qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * d, rows, 3 * d, TCA_HD,
+  GN_PROPAGATE(make_tensor_map_2d(&tmQ, a.qkv, H16<H>::TMAP, 2, 3 * d, rows, 3 * d, TCA_HD,
                                   TCA_QROWS, sw));
-  GN_PROPAGATE(make_tensor_map_2d(&tmKV, a.qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * d, rows, 3 * d, TCA_HD, SK, sw));
-  GN_PROPAGATE(make_tensor_map_2d(&tmO, a.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d, rows, d, TCA_HD, TCA_QROWS, sw));
+  GN_PROPAGATE(make_tensor_map_2d(&tmKV, a.qkv, H16<H>::TMAP, 2, 3 * d, rows, 3 * d, TCA_HD, SK, sw));
+  GN_PROPAGATE(make_tensor_map_2d(&tmO, a.out, H16<H>::TMAP, 2, d, rows, d, TCA_HD, TCA_QROWS, sw));
   const int smem = (TCA_QROWS + 2 * SK) * TCA_ROWB + 64 + 4 * TCA_QROWS * 4 + 1024;
-  auto kern = spatial_attn_tc_kernel<SK>;
+  auto kern = spatial_attn_tc_kernel<SK, H>;
   static bool attr_set = false;
   if (!attr_set) {
     GN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -287,13 +287,14 @@ struct TcpBars {
   uint32_t tmem_slot, pad;
 };
 
+template <typename H>
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 spatial_attn_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmO,
                                   int d, int n_heads, int n_items, float scale_log2e) {
   constexpr int SK = TCP_SK;
   constexpr int BK = SK / 2;          // keys per softmax block
-  constexpr uint32_t IDESC_QK = umma_idesc(UMMA_FMT_BF16, TCA_QROWS, SK, 0, 0);
-  constexpr uint32_t IDESC_PV = umma_idesc(UMMA_FMT_BF16, TCA_QROWS, TCA_HD, 0, 1);
+  constexpr uint32_t IDESC_QK = umma_idesc(H16<H>::UMMA_FMT, TCA_QROWS, SK, 0, 0);
+  constexpr uint32_t IDESC_PV = umma_idesc(H16<H>::UMMA_FMT, TCA_QROWS, TCA_HD, 0, 1);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -442,8 +443,8 @@ spatial_attn_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmKV, cons
             const float p2 = ex2_approx(fmaf(__uint_as_float(r[c * 32 + 2 * e + 2]), scale_log2e, -off));
             const float p3 = ex2_approx(fmaf(__uint_as_float(r[c * 32 + 2 * e + 3]), scale_log2e, -off));
             l0 += p0; l1 += p1; l2 += p2; l3 += p3;
-            pk[e] = pack_bf16x2(p0, p1);
-            pk[e + 1] = pack_bf16x2(p2, p3);
+            pk[e] = pack_h2<H>(p0, p1);
+            pk[e + 1] = pack_h2<H>(p2, p3);
           }
           tmem_st_32x32b_x16(my_addr + blk * BK + c * 16, pk);   // over the block's own, already loaded scores
         }
@@ -482,10 +483,10 @@ spatial_attn_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmKV, cons
           for (int e = 0; e < 8; ++e)
             o[e] = fmaf(__uint_as_float(ra[8 * c + e]), wa, __uint_as_float(rb[8 * c + e]) * wb);
           uint4 v;
-          v.x = pack_bf16x2(o[0], o[1]);
-          v.y = pack_bf16x2(o[2], o[3]);
-          v.z = pack_bf16x2(o[4], o[5]);
-          v.w = pack_bf16x2(o[6], o[7]);
+          v.x = pack_h2<H>(o[0], o[1]);
+          v.y = pack_h2<H>(o[2], o[3]);
+          v.z = pack_h2<H>(o[4], o[5]);
+          v.w = pack_h2<H>(o[6], o[7]);
           *reinterpret_cast<uint4*>(srow + ((c ^ (row & 7)) << 4)) = v;
         }
       }
@@ -508,20 +509,21 @@ spatial_attn_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmKV, cons
   }
 }
 
+template <typename H>
 int launch_tc_persistent(const AttnArgs& a, int n_frames, cudaStream_t st) {
   const int d = a.n_heads * a.head_dim;
   const int64_t rows = (int64_t)n_frames * TCP_SK;
   CUtensorMap tmKV, tmO;
   const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
-  GN_PROPAGATE(make_tensor_map_2d(&tmKV, a.qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * d, rows, 3 * d, TCA_HD, TCP_SK,
+  GN_PROPAGATE(make_tensor_map_2d(&tmKV, a.qkv, H16<H>::TMAP, 2, 3 * d, rows, 3 * d, TCA_HD, TCP_SK,
                                   sw));
-  GN_PROPAGATE(make_tensor_map_2d(&tmO, a.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d, rows, d, TCA_HD, TCA_QROWS, sw));
+  GN_PROPAGATE(make_tensor_map_2d(&tmO, a.out, H16<H>::TMAP, 2, d, rows, d, TCA_HD, TCA_QROWS, sw));
   const int smem = TCP_STAGES * TCP_STAGE_BYTES + (int)sizeof(TcpBars) + 1024;
   static bool attr_set = false;
   static int sms = 0;
   if (!attr_set) {
-    GN_CUDA_CHECK(cudaFuncSetAttribute(spatial_attn_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       smem));
+    GN_CUDA_CHECK(cudaFuncSetAttribute(spatial_attn_tc_persistent_kernel<H>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -530,8 +532,8 @@ int launch_tc_persistent(const AttnArgs& a, int n_frames, cudaStream_t st) {
   }
   const int n_items = n_frames * a.n_heads;
   const int grid = n_items < sms ? n_items : sms;
-  GN_CUDA_CHECK(launch_kernel(PC_SPATIAL, spatial_attn_tc_persistent_kernel, dim3(grid), dim3(TCP_THREADS), (size_t)smem,
-                              st, tmKV, tmO, d, a.n_heads, n_items, a.scale * 1.4426950408889634f));
+  GN_CUDA_CHECK(launch_kernel(PC_SPATIAL, spatial_attn_tc_persistent_kernel<H>, dim3(grid), dim3(TCP_THREADS),
+                              (size_t)smem, st, tmKV, tmO, d, a.n_heads, n_items, a.scale * 1.4426950408889634f));
   ++g_launch_count;
   return GN_OK;
 }
@@ -548,8 +550,12 @@ int tc_spatial_attention(const AttnArgs& a, int n_frames, int S, cudaStream_t st
   // GENIE_B200_SPATIAL_TC: unset / 2 = persistent kernel for S = 256, 1 = one-CTA-per-tile kernel, 0 = mma.sync kernel
   const char* e = getenv("GENIE_B200_SPATIAL_TC");
   const bool persistent = !(e && e[0] == '1');
-  if (S == 256) return persistent ? launch_tc_persistent(a, n_frames, st) : launch_tc_t<256>(a, n_frames, st);
-  return launch_tc_t<128>(a, n_frames, st);
+  if (a.fp16) {
+    if (S == 256) return persistent ? launch_tc_persistent<f16>(a, n_frames, st) : launch_tc_t<256, f16>(a, n_frames, st);
+    return launch_tc_t<128, f16>(a, n_frames, st);
+  }
+  if (S == 256) return persistent ? launch_tc_persistent<bf16>(a, n_frames, st) : launch_tc_t<256, bf16>(a, n_frames, st);
+  return launch_tc_t<128, bf16>(a, n_frames, st);
 }
 
 }  // namespace gn

@@ -7,10 +7,30 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace gn {
 
 typedef __nv_bfloat16 bf16;
+typedef __half f16;
+
+// The 16-bit tensor-core paths are written once and instantiated for both 16-bit formats (tcgen05 kind::f16 takes
+// either): bf16 (8-bit mantissa, fp32 range) and IEEE fp16 (11-bit mantissa = the tf32 mantissa, +-65504).  fp16 is the
+// parity format: with fp32 accumulation / residual / LayerNorm / softmax it meets the 1e-3 logits bar that bf16 cannot
+// (scripts/precision_budget.py); conversions saturate to the largest finite value instead of overflowing to inf.
+template <typename H> struct H16;
+template <> struct H16<bf16> {
+  static constexpr uint32_t UMMA_FMT = 1;   // UMMA_FMT_BF16
+  static constexpr CUtensorMapDataType TMAP = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+};
+template <> struct H16<f16> {
+  static constexpr uint32_t UMMA_FMT = 0;   // UMMA_FMT_F16
+  static constexpr CUtensorMapDataType TMAP = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+};
+template <> struct H16<float> {            // fp32 operands run as kind::tf32
+  static constexpr uint32_t UMMA_FMT = 2;   // UMMA_FMT_TF32
+  static constexpr CUtensorMapDataType TMAP = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+};
 
 // ---- error plumbing (thread-local message, negative return codes; never throws across the C ABI)
 enum : int {
@@ -151,6 +171,8 @@ template <>
 __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+template <>
+__device__ __forceinline__ float to_f32<f16>(f16 v) { return __half2float(v); }
 
 template <typename T>
 __device__ __forceinline__ T from_f32(float v);
@@ -158,6 +180,38 @@ template <>
 __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ f16 from_f32<f16>(float v) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+  return __ushort_as_half(r);
+}
+
+// two fp32 -> one packed 16-bit pair (lo in bits [0,16)), round to nearest even
+template <typename H>
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi);
+template <>
+__device__ __forceinline__ uint32_t pack_h2<bf16>(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <>
+__device__ __forceinline__ uint32_t pack_h2<f16>(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <typename H>
+__device__ __forceinline__ float2 unpack_h2(uint32_t v);
+template <>
+__device__ __forceinline__ float2 unpack_h2<bf16>(uint32_t v) {
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+template <>
+__device__ __forceinline__ float2 unpack_h2<f16>(uint32_t v) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
 
 // round-to-nearest fp32 -> tf32 (tcgen05 kind::tf32 TRUNCATES its fp32 operands, which biases every product
 // by ~2^-11; operands are therefore pre-rounded wherever they are produced in the tf32 parity mode)

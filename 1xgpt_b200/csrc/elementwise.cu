@@ -2,6 +2,7 @@
 // LayerNorm / cast "prep" that feeds the GEMM A operand, frame gather for the readout.
 // One warp per token row, 16-byte accesses, fp32 statistics via warp shuffles.
 #include "kernels.cuh"
+#include <type_traits>
 
 namespace gn {
 
@@ -120,9 +121,10 @@ prep_kernel(const float* __restrict__ x, OutT* __restrict__ out, const float* __
         if (round_tf32) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
         reinterpret_cast<float4*>(out + (int64_t)row * d)[c] = o;
       } else {
+        typedef typename std::conditional<sizeof(OutT) == 2, OutT, bf16>::type P16;
         uint2 p;
-        p.x = pack_bf16x2(o.x, o.y);
-        p.y = pack_bf16x2(o.z, o.w);
+        p.x = pack_h2<P16>(o.x, o.y);
+        p.y = pack_h2<P16>(o.z, o.w);
         reinterpret_cast<uint2*>(out + (int64_t)row * d)[c] = p;
       }
     }
@@ -156,6 +158,7 @@ int launch_prep(const float* x, void* out, int out_bf16, const float* gamma, con
                 float scale, int S, int Tact, int tsel, cudaStream_t st, int round_tf32) {
   GN_REQUIRE(d % 4 == 0, "prep: d_model must be a multiple of 4");
   GN_REQUIRE((gamma == nullptr) == (beta == nullptr), "prep: gamma/beta must both be set or both be null");
+  if (out_bf16 == 2) return launch_prep_t<f16>(x, static_cast<f16*>(out), gamma, beta, n_rows, d, scale, S, Tact, tsel, st, 0);
   if (out_bf16) return launch_prep_t<bf16>(x, static_cast<bf16*>(out), gamma, beta, n_rows, d, scale, S, Tact, tsel, st, 0);
   return launch_prep_t<float>(x, static_cast<float*>(out), gamma, beta, n_rows, d, scale, S, Tact, tsel, st, round_tf32);
 }
@@ -224,10 +227,11 @@ int launch_fold_ln(const float* W, const float* gamma, const float* beta, const 
 // -------------------------------------------------------------------------------------
 // fp32 -> bf16 weight conversion (weights are repacked once at load time)
 // -------------------------------------------------------------------------------------
-__global__ void cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int64_t n) {
+template <typename H>
+__global__ void cast_h16_kernel(const float* __restrict__ in, H* __restrict__ out, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) out[i] = __float2bfloat16_rn(in[i]);
+  for (; i < n; i += stride) out[i] = from_f32<H>(in[i]);
 }
 __global__ void round_tf32_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -241,10 +245,11 @@ int launch_round_tf32(const float* in, float* out, int64_t n, cudaStream_t st) {
   GN_CUDA_CHECK(cudaGetLastError());
   return GN_OK;
 }
-int launch_cast_bf16(const float* in, bf16* out, int64_t n, cudaStream_t st) {
+int launch_cast_h16(const float* in, void* out, int fp16, int64_t n, cudaStream_t st) {
   if (n == 0) return GN_OK;
   const int grid = (int)(ceil_div64(n, 256) < 4096 ? ceil_div64(n, 256) : 4096);
-  cast_bf16_kernel<<<grid, 256, 0, st>>>(in, out, n);
+  if (fp16) cast_h16_kernel<f16><<<grid, 256, 0, st>>>(in, static_cast<f16*>(out), n);
+  else cast_h16_kernel<bf16><<<grid, 256, 0, st>>>(in, static_cast<bf16*>(out), n);
   GN_CUDA_CHECK(cudaGetLastError());
   return GN_OK;
 }

@@ -8,6 +8,10 @@
 namespace gn {
 
 unsigned long long g_launch_count = 0;
+// launches that left the intended Blackwell kernel for a slower variant because of a shape / alignment / precision
+// cliff (CUDA-core GEMM without force_simt, generic or mma.sync attention where the tcgen05 / TMA kernel was expected).
+// Tests assert that it stays 0 on the production shapes (gn_fallback_launches()).
+unsigned long long g_fallback_launches = 0;
 
 static bool env_on(const char* name, bool dflt) {
   const char* v = getenv(name);
@@ -118,34 +122,46 @@ __device__ __forceinline__ void stage_row_chunk<float>(uint8_t* buf, uint32_t la
     *reinterpret_cast<float4*>(row + ((j ^ (lane & 7)) << 4)) = f;
   }
 }
-// bf16: 32 cols = 64 B per row, SWIZZLE_64B (16B chunk index ^= (row >> 1) & 3)
-template <>
-__device__ __forceinline__ void stage_row_chunk<bf16>(uint8_t* buf, uint32_t lane, const float (&v)[EPI_COLS]) {
+// 16-bit (bf16 / fp16): 32 cols = 64 B per row, SWIZZLE_64B (16B chunk index ^= (row >> 1) & 3)
+template <typename H>
+__device__ __forceinline__ void stage_row_chunk16(uint8_t* buf, uint32_t lane, const float (&v)[EPI_COLS]) {
   uint8_t* row = buf + lane * 64;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     uint4 p;
-    p.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-    p.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-    p.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-    p.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+    p.x = pack_h2<H>(v[8 * j + 0], v[8 * j + 1]);
+    p.y = pack_h2<H>(v[8 * j + 2], v[8 * j + 3]);
+    p.z = pack_h2<H>(v[8 * j + 4], v[8 * j + 5]);
+    p.w = pack_h2<H>(v[8 * j + 6], v[8 * j + 7]);
     *reinterpret_cast<uint4*>(row + ((j ^ ((lane >> 1) & 3)) << 4)) = p;
   }
 }
+template <>
+__device__ __forceinline__ void stage_row_chunk<bf16>(uint8_t* buf, uint32_t lane, const float (&v)[EPI_COLS]) {
+  stage_row_chunk16<bf16>(buf, lane, v);
+}
+template <>
+__device__ __forceinline__ void stage_row_chunk<f16>(uint8_t* buf, uint32_t lane, const float (&v)[EPI_COLS]) {
+  stage_row_chunk16<f16>(buf, lane, v);
+}
 
-// bf16, wide staging: 64 cols = 128 B per row, SWIZZLE_128B; `half` selects the left / right 32 columns
+// 16-bit, wide staging: 64 cols = 128 B per row, SWIZZLE_128B; `half` selects the left / right 32 columns
+template <typename H>
 __device__ __forceinline__ void stage_row_chunk_wide(uint8_t* buf, uint32_t lane, int half, const float (&v)[EPI_COLS]) {
   uint8_t* row = buf + lane * 128;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     uint4 p;
-    p.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-    p.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-    p.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-    p.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+    p.x = pack_h2<H>(v[8 * j + 0], v[8 * j + 1]);
+    p.y = pack_h2<H>(v[8 * j + 2], v[8 * j + 3]);
+    p.z = pack_h2<H>(v[8 * j + 4], v[8 * j + 5]);
+    p.w = pack_h2<H>(v[8 * j + 6], v[8 * j + 7]);
     *reinterpret_cast<uint4*>(row + (((half * 4 + j) ^ (lane & 7)) << 4)) = p;
   }
 }
+// the 16-bit type that goes with an operand type: itself for bf16 / fp16, bf16 for fp32 (tf32) operands
+template <typename InT> struct Half16Of { typedef InT type; };
+template <> struct Half16Of<float> { typedef bf16 type; };
 
 template <typename InT, int BLOCK_N, int EPI, typename OutT, bool DUAL, int CTAS, bool QKN>
 __global__ void __launch_bounds__(32 * (2 + EpiCfg<EPI>::WARPS), 1)
@@ -158,8 +174,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr int STAGES = SM::STAGES;
   constexpr int BLOCK_K = TILE_K_BYTES / (int)sizeof(InT);     // 64 (bf16) or 32 (tf32)
   constexpr int TMEM_COLS = NUM_ACC_STAGES * BLOCK_N;          // 128 / 256 / 512
-  constexpr uint32_t IDESC =
-      umma_idesc(sizeof(InT) == 2 ? UMMA_FMT_BF16 : UMMA_FMT_TF32, BLOCK_M * CTAS, BLOCK_N);
+  constexpr uint32_t IDESC = umma_idesc(H16<InT>::UMMA_FMT, BLOCK_M * CTAS, BLOCK_N);
+  typedef typename Half16Of<InT>::type CopyT;   // type of the 16-bit copy of the residual stream (DUAL)
   // CTA pair: rank within the pair, pair index, number of pairs (CTAS == 1: rank 0, one "pair" per CTA)
   const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
   const int pair = (int)blockIdx.x / CTAS;
@@ -446,7 +462,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < EPI_COLS; ++j) { rs1 += v[j]; rs2 = fmaf(v[j], v[j], rs2); }
           }
-          if (DUAL) stage_row_chunk<bf16>(st1 + (g & 1) * SM::OUT2_STAGE_BYTES, lane, v);
+          if (DUAL) stage_row_chunk<CopyT>(st1 + (g & 1) * SM::OUT2_STAGE_BYTES, lane, v);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -532,7 +548,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // qk-LayerNorm: the two chunks of a pair are the 64 columns of one head of this thread's row
             const bool qkn = QKN && (col0 - half * EPI_COLS) < args.qkn_cols;
             if constexpr (!QKN) {
-              if (!(args.dbg & 8)) stage_row_chunk_wide(st0 + buf * SM::OUT_STAGE_BYTES, lane, half, v);
+              if (!(args.dbg & 8)) stage_row_chunk_wide<OutT>(st0 + buf * SM::OUT_STAGE_BYTES, lane, half, v);
             } else if (qkn) {
               if (half == 0) {
 #pragma unroll
@@ -565,11 +581,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                   v[4 * j + 2] = (v[4 * j + 2] - mean) * rstd * gb.z + bb.z;
                   v[4 * j + 3] = (v[4 * j + 3] - mean) * rstd * gb.w + bb.w;
                 }
-                stage_row_chunk_wide(st0 + buf * SM::OUT_STAGE_BYTES, lane, 0, vsave);
-                stage_row_chunk_wide(st0 + buf * SM::OUT_STAGE_BYTES, lane, 1, v);
+                stage_row_chunk_wide<OutT>(st0 + buf * SM::OUT_STAGE_BYTES, lane, 0, vsave);
+                stage_row_chunk_wide<OutT>(st0 + buf * SM::OUT_STAGE_BYTES, lane, 1, v);
               }
             } else if (!(args.dbg & 8)) {
-              stage_row_chunk_wide(st0 + buf * SM::OUT_STAGE_BYTES, lane, half, v);
+              stage_row_chunk_wide<OutT>(st0 + buf * SM::OUT_STAGE_BYTES, lane, half, v);
             }
             if (half == 1) {
               fence_proxy_async_smem();
@@ -634,9 +650,9 @@ template <typename InT, int BLOCK_N, int EPI, typename OutT, bool DUAL, int CTAS
 int launch_tc(const LinearArgs& a, cudaStream_t stream) {
   using SM = GemmSmem<BLOCK_N, EPI, OutT, DUAL, CTAS>;
   constexpr int BLOCK_K = TILE_K_BYTES / (int)sizeof(InT);
-  const CUtensorMapDataType in_dt = sizeof(InT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  const CUtensorMapDataType out_dt =
-      sizeof(OutT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapDataType in_dt = H16<InT>::TMAP;
+  const CUtensorMapDataType out_dt = H16<OutT>::TMAP;
+  const CUtensorMapDataType copy_dt = H16<typename Half16Of<InT>::type>::TMAP;
   CUtensorMap tmA, tmB, tmO, tmO2, tmR, tmK, tmV;
   int tw = 0, th = 0;
   if (a.conv) {
@@ -655,8 +671,8 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
                                   (sizeof(OutT) == 2 && !SM::WIDE) ? CU_TENSOR_MAP_SWIZZLE_64B
                                                                    : CU_TENSOR_MAP_SWIZZLE_128B));
   if (DUAL) {
-    GN_PROPAGATE(make_tensor_map_2d(&tmO2, a.out2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.N, a.M, a.ldo2, EPI_COLS,
-                                    32, CU_TENSOR_MAP_SWIZZLE_64B));
+    GN_PROPAGATE(make_tensor_map_2d(&tmO2, a.out2, copy_dt, 2, a.N, a.M, a.ldo2, EPI_COLS, 32,
+                                    CU_TENSOR_MAP_SWIZZLE_64B));
   } else {
     tmO2 = tmO;
   }
@@ -679,8 +695,8 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
     }
     const int box[4] = {SM::WIDE ? 2 * EPI_COLS : EPI_COLS, 1, 1, 32};
     const CUtensorMapSwizzle ksw = SM::WIDE ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    GN_PROPAGATE(make_tensor_map_nd(&tmK, a.kv_k, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, str, box, ksw));
-    GN_PROPAGATE(make_tensor_map_nd(&tmV, a.kv_v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, str, box, ksw));
+    GN_PROPAGATE(make_tensor_map_nd(&tmK, a.kv_k, out_dt, 4, dims, str, box, ksw));
+    GN_PROPAGATE(make_tensor_map_nd(&tmV, a.kv_v, out_dt, 4, dims, str, box, ksw));
   } else {
     tmK = tmO;
     tmV = tmO;
@@ -755,15 +771,16 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
 
 template <typename InT, int BLOCK_N, int CTAS = 1>
 int dispatch_epi(const LinearArgs& a, cudaStream_t s) {
+  typedef typename Half16Of<InT>::type O16;   // 16-bit outputs share the operands' 16-bit format
   if (a.epi == EPI_STORE) {
     if constexpr (sizeof(InT) == 2 && BLOCK_N >= 128) {
-      if (a.out_bf16 && a.qkn_gamma) return launch_tc<InT, BLOCK_N, EPI_STORE, bf16, false, CTAS, true>(a, s);
+      if (a.out_bf16 && a.qkn_gamma) return launch_tc<InT, BLOCK_N, EPI_STORE, O16, false, CTAS, true>(a, s);
     }
-    return a.out_bf16 ? launch_tc<InT, BLOCK_N, EPI_STORE, bf16, false, CTAS>(a, s)
+    return a.out_bf16 ? launch_tc<InT, BLOCK_N, EPI_STORE, O16, false, CTAS>(a, s)
                       : launch_tc<InT, BLOCK_N, EPI_STORE, float, false, CTAS>(a, s);
   }
   if (a.epi == EPI_GELU) {
-    return a.out_bf16 ? launch_tc<InT, BLOCK_N, EPI_GELU, bf16, false, CTAS>(a, s)
+    return a.out_bf16 ? launch_tc<InT, BLOCK_N, EPI_GELU, O16, false, CTAS>(a, s)
                       : launch_tc<InT, BLOCK_N, EPI_GELU, float, false, CTAS>(a, s);
   }
   if (a.epi == EPI_RESID) {
@@ -805,7 +822,8 @@ template <typename InT, typename OutT>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const InT* __restrict__ A, int64_t lda, const InT* __restrict__ W, int64_t ldw,
                  const float* __restrict__ bias, const float* __restrict__ resid, int64_t ldr, OutT* __restrict__ out,
-                 int64_t ldo, bf16* __restrict__ out2, int64_t ldo2, int M, int N, int K, int epi) {
+                 int64_t ldo, typename Half16Of<InT>::type* __restrict__ out2, int64_t ldo2, int M, int N, int K,
+                 int epi) {
   __shared__ float sa[SK][ST + 1];
   __shared__ float sw[SK][ST + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -844,7 +862,7 @@ gemm_simt_kernel(const InT* __restrict__ A, int64_t lda, const InT* __restrict__
       if (epi == EPI_GELU) v = gelu_erf(v);
       if (epi == EPI_RESID) v += resid[(int64_t)gm * ldr + gn];
       out[(int64_t)gm * ldo + gn] = from_f32<OutT>(v);
-      if (out2) out2[(int64_t)gm * ldo2 + gn] = __float2bfloat16_rn(v);
+      if (out2) out2[(int64_t)gm * ldo2 + gn] = from_f32<typename Half16Of<InT>::type>(v);
     }
   }
 }
@@ -854,7 +872,8 @@ int launch_simt(const LinearArgs& a, cudaStream_t s) {
   dim3 grid(ceil_div(a.N, ST), ceil_div(a.M, ST));
   gemm_simt_kernel<InT, OutT><<<grid, 256, 0, s>>>(
       static_cast<const InT*>(a.A), a.lda, static_cast<const InT*>(a.W), a.ldw, a.bias, a.resid, a.ldr,
-      static_cast<OutT*>(a.out), a.ldo, static_cast<bf16*>(a.out2), a.ldo2, a.M, a.N, a.K, a.epi);
+      static_cast<OutT*>(a.out), a.ldo, static_cast<typename Half16Of<InT>::type*>(a.out2), a.ldo2, a.M, a.N, a.K,
+      a.epi);
   GN_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;
   return GN_OK;
@@ -913,11 +932,17 @@ int linear_forward(const LinearArgs& a, cudaStream_t stream) {
                      (!a.resid || reinterpret_cast<uintptr_t>(a.resid) % 16 == 0) &&
                      (!a.bias || reinterpret_cast<uintptr_t>(a.bias) % 16 == 0) &&
                      !(a.out2 && (a.epi != EPI_RESID || a.out_bf16));
-  if (tc_ok) return a.in_bf16 ? dispatch_n<bf16>(a, stream) : dispatch_n<float>(a, stream);
+  if (tc_ok) {
+    if (!a.in_bf16) return dispatch_n<float>(a, stream);
+    return a.fp16 ? dispatch_n<f16>(a, stream) : dispatch_n<bf16>(a, stream);
+  }
   GN_REQUIRE(!a.kv_k, "K/V-cache output: operands not eligible for the tensor path");
   GN_REQUIRE(!a.qkn_gamma, "qk-LayerNorm epilogue: operands not eligible for the tensor path");
-  if (a.in_bf16)
+  if (!a.force_simt) ++g_fallback_launches;   // CUDA-core GEMM on a handle that did not ask for the fp32 mode: shape / alignment cliff
+  if (a.in_bf16) {
+    if (a.fp16) return a.out_bf16 ? launch_simt<f16, f16>(a, stream) : launch_simt<f16, float>(a, stream);
     return a.out_bf16 ? launch_simt<bf16, bf16>(a, stream) : launch_simt<bf16, float>(a, stream);
+  }
   return a.out_bf16 ? launch_simt<float, bf16>(a, stream) : launch_simt<float, float>(a, stream);
 }
 

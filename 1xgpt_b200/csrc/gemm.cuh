@@ -40,8 +40,9 @@ struct LinearArgs {
   int64_t ldo2;
   int M, N, K;
   int epi;            // EpiKind
-  int in_bf16;        // 1: A/W bf16 (kind::f16), 0: f32 (kind::tf32 on the tensor path)
-  int out_bf16;       // 1: out is bf16, 0: f32
+  int in_bf16;        // 1: A/W are 16-bit (kind::f16), 0: f32 (kind::tf32 on the tensor path)
+  int out_bf16;       // 1: out is 16-bit (same format as A/W), 0: f32
+  int fp16;           // 16-bit tensors are IEEE fp16 instead of bf16 (the parity format, see common.cuh H16)
   int force_simt;     // 1: CUDA-core fp32 path regardless of shape
   int round_out_tf32; // 1: round the fp32 output to tf32 (it feeds a kind::tf32 GEMM next)
   // qk-LayerNorm (attention.py:42-47: LayerNorm(head_dim) with one shared affine on q and k) applied in the epilogue of
@@ -84,5 +85,7 @@ int resid_block_n(int N, int K, bool dual);
 
 // number of kernels launched by linear_forward so far (bench's gpu_launches accounting)
 extern unsigned long long g_launch_count;
+// launches that fell off the intended Blackwell kernel onto a slower variant (see gemm.cu)
+extern unsigned long long g_fallback_launches;
 
 }  // namespace gn

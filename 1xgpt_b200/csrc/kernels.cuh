@@ -10,6 +10,7 @@ namespace gn {
 // ---- elementwise.cu
 int launch_embed(const int32_t* ids, const float* E, const float* mask_embed, const float* pos, float* x, int B,
                  int T, int S, int t0, int Tact, int d, int V, int NV, int mask_id, cudaStream_t st);
+// out_bf16: 0 = fp32 output, 1 = bf16, 2 = fp16
 int launch_prep(const float* x, void* out, int out_bf16, const float* gamma, const float* beta, int n_rows, int d,
                 float scale, int S, int Tact, int tsel, cudaStream_t st, int round_tf32 = 0);
 // prep variant that also writes the row statistics {sum, sumsq} (1 partial per row) next to the bf16 cast
@@ -18,7 +19,7 @@ int launch_prep_stats(const float* x, bf16* out, float* stats, int n_rows, int d
 // bias_f[n] = sum_k beta[k] * W[n,k] + bias[n]
 int launch_fold_ln(const float* W, const float* gamma, const float* beta, const float* bias, bf16* Wf, float* colsum,
                    float* bias_f, int N, int K, cudaStream_t st);
-int launch_cast_bf16(const float* in, bf16* out, int64_t n, cudaStream_t st);
+int launch_cast_h16(const float* in, void* out, int fp16, int64_t n, cudaStream_t st);   // fp32 -> bf16 / fp16
 int launch_round_tf32(const float* in, float* out, int64_t n, cudaStream_t st);
 int launch_logits_transpose(const float* rows, float* out, int B, int Tl, int S, int C, int Tout, int tslot0,
                             cudaStream_t st);
@@ -27,7 +28,8 @@ int launch_logits_transpose(const float* rows, float* out, int B, int Tl, int S,
 struct AttnArgs {
   const void* qkv;        // [n_seq * n_q_tok(+..), 3*d] fused projection output, column order (3, h, hd)
   void* out;              // [rows, d]
-  int act_bf16;           // activation dtype of qkv/out: 1 bf16, 0 f32
+  int act_bf16;           // activation dtype of qkv/out: 1 = 16-bit, 0 = f32
+  int fp16;               // 16-bit activations are IEEE fp16 instead of bf16
   int n_heads, head_dim;
   float scale;
   const float* qk_gamma;  // [hd] shared q/k LayerNorm affine (attention.py:34,43-44) or nullptr

@@ -41,7 +41,9 @@ struct LayerW {
 struct gn_model {
   gn_config cfg;
   int device = 0;
-  int act_bf16 = 1;     // activation / weight-matrix dtype between kernels
+  int act_bf16 = 1;     // activations / weight matrices between kernels are 16-bit (bf16 or fp16)
+  int fp16 = 0;         // ... and that 16-bit format is IEEE fp16 (GN_PREC_FP16) instead of bf16
+  int o16() const { return act_bf16 ? (fp16 ? 2 : 1) : 0; }   // launch_prep output code
   int force_simt = 0;
   int tf32 = 0;         // tcgen05 kind::tf32 parity mode: every GEMM operand is pre-rounded to tf32 (RN)
   int hid = 0, C = 0;   // mlp hidden, readout width NV*V
@@ -255,7 +257,7 @@ int linear(gn_model* m, const void* A, int64_t lda, const void* W, int K, const 
   }
   la.A = A; la.lda = lda; la.W = W; la.ldw = K; la.bias = bias; la.resid = resid; la.ldr = N;
   la.out = out; la.ldo = ldo; la.out2 = out2; la.ldo2 = N;
-  la.M = M; la.N = N; la.K = K; la.epi = epi; la.in_bf16 = m->act_bf16; la.out_bf16 = out_bf16;
+  la.M = M; la.N = N; la.K = K; la.epi = epi; la.in_bf16 = m->act_bf16; la.out_bf16 = out_bf16; la.fp16 = m->fp16;
   la.force_simt = m->force_simt;
   // The attention output and the MLP hidden are read by exactly one GEMM whose N = d spans only one or two column
   // tiles: load them evict_first so that the residual stream, the weights and the outputs being written stay in L2.
@@ -393,7 +395,7 @@ int run_layers_body(gn_model* m, int b0, int nb, int t0, int Tact, bool use_cach
       GN_PROPAGATE(linear(m, m->a, d, w.qkv_s_f, d, w.qkv_s_bf, nullptr, m->big, 3 * d, nullptr, n, 3 * d, EPI_STORE, 1,
                           st, &lf));
       AttnArgs aa{};
-      aa.qkv = m->big; aa.out = m->o; aa.act_bf16 = 1; aa.n_heads = H; aa.head_dim = hd; aa.scale = scale;
+      aa.qkv = m->big; aa.out = m->o; aa.act_bf16 = 1; aa.fp16 = m->fp16; aa.n_heads = H; aa.head_dim = hd; aa.scale = scale;
       GN_PROPAGATE(launch_spatial_attention(aa, nb * Tact, S, c.generic_attention, st));
       m->flops_executed += 4.0 * S * (double)d * n;
       GN_PROPAGATE(linear(m, m->o, d, w.attn[0].proj_w, d, w.attn[0].proj_b, m->x, m->x, d, m->a, n, d, EPI_RESID, 0, st));
@@ -420,10 +422,10 @@ int run_layers_body(gn_model* m, int b0, int nb, int t0, int Tact, bool use_cach
     // ---------------- spatial attention: x += proj(attn(qkv(norm1(x))))
     const void* ain;
     if (!c.qk_norm) {
-      GN_PROPAGATE(launch_prep(m->x, m->a, bf, w.ln1_g, w.ln1_b, n, d, 1.f, S, Tact, -1, st, tf));
+      GN_PROPAGATE(launch_prep(m->x, m->a, m->o16(), w.ln1_g, w.ln1_b, n, d, 1.f, S, Tact, -1, st, tf));
       ain = m->a;
     } else if (cp) {
-      if (!a_is_x) GN_PROPAGATE(launch_prep(m->x, m->a, bf, nullptr, nullptr, n, d, 1.f, S, Tact, -1, st, tf));
+      if (!a_is_x) GN_PROPAGATE(launch_prep(m->x, m->a, m->o16(), nullptr, nullptr, n, d, 1.f, S, Tact, -1, st, tf));
       ain = m->a;
     } else {
       ain = m->x;
@@ -431,7 +433,7 @@ int run_layers_body(gn_model* m, int b0, int nb, int t0, int Tact, bool use_cach
     GN_PROPAGATE(linear(m, ain, d, w.attn[0].qkv_w, d, w.attn[0].qkv_b, nullptr, m->big, 3 * d, nullptr, n, 3 * d,
                         EPI_STORE, bf, st, nullptr, nullptr, &w.attn[0]));
     AttnArgs aa{};
-    aa.qkv = m->big; aa.out = m->o; aa.act_bf16 = bf; aa.n_heads = H; aa.head_dim = hd; aa.scale = scale;
+    aa.qkv = m->big; aa.out = m->o; aa.act_bf16 = bf; aa.fp16 = m->fp16; aa.n_heads = H; aa.head_dim = hd; aa.scale = scale;
     aa.round_tf32 = tf;
     if (!m->qkn_epi) { aa.qk_gamma = w.attn[0].norm_g; aa.qk_beta = w.attn[0].norm_b; }
     GN_PROPAGATE(launch_spatial_attention(aa, nb * Tact, S, c.generic_attention || !bf, st));
@@ -448,7 +450,7 @@ int run_layers_body(gn_model* m, int b0, int nb, int t0, int Tact, bool use_cach
                         d, EPI_RESID, 0, st));
     // ---------------- MLP: x += fc2(gelu(fc1(norm2(x))))
     if (!c.qk_norm) {
-      GN_PROPAGATE(launch_prep(m->x, m->a, bf, w.ln2_g, w.ln2_b, n, d, 1.f, S, Tact, -1, st, tf));
+      GN_PROPAGATE(launch_prep(m->x, m->a, m->o16(), w.ln2_g, w.ln2_b, n, d, 1.f, S, Tact, -1, st, tf));
       ain = m->a;
     } else if (cp) {
       if (tf) GN_PROPAGATE(launch_prep(m->x, m->a, 0, nullptr, nullptr, n, d, 1.f, S, Tact, -1, st, 1));
@@ -528,7 +530,7 @@ int readout(gn_model* m, int nb, int Tact, int tsel, float* out_rows, cudaStream
   if (!m->act_bf16 && !m->tf32 && tsel < 0 && mult == 1.0f) {
     ain = m->x;
   } else {
-    GN_PROPAGATE(launch_prep(m->x, m->a, m->act_bf16, nullptr, nullptr, R, c.d_model, mult, c.S, Tact, tsel, st,
+    GN_PROPAGATE(launch_prep(m->x, m->a, m->o16(), nullptr, nullptr, R, c.d_model, mult, c.S, Tact, tsel, st,
                              m->tf32));
     ain = m->a;
   }
@@ -670,6 +672,7 @@ extern "C" {
 int gn_version(void) { return GN_ABI_VERSION; }
 const char* gn_last_error(void) { return gn::last_error(); }
 uint64_t gn_kernel_launches(void) { return gn::g_launch_count; }
+uint64_t gn_fallback_launches(void) { return gn::g_fallback_launches; }
 
 int gn_model_create(gn_model** out, const gn_config* cfg, int device) {
   GN_REQUIRE(out && cfg, "gn_model_create: null argument");
@@ -688,7 +691,7 @@ int gn_model_create(gn_model** out, const gn_config* cfg, int device) {
     for (int i = 0; i < cfg->num_factored_vocabs; ++i) p *= cfg->factored_vocab_size;
     GN_REQUIRE(p == cfg->image_vocab_size, "factored_vocab_size ** num_factored_vocabs != image_vocab_size");
   }
-  GN_REQUIRE(cfg->precision >= GN_PREC_BF16 && cfg->precision <= GN_PREC_FP32, "unknown precision %d", cfg->precision);
+  GN_REQUIRE(cfg->precision >= GN_PREC_BF16 && cfg->precision <= GN_PREC_FP16, "unknown precision %d", cfg->precision);
   int ndev = 0;
   GN_CUDA_CHECK(cudaGetDeviceCount(&ndev));
   GN_REQUIRE(device >= 0 && device < ndev, "device %d not available (%d visible)", device, ndev);
@@ -700,15 +703,16 @@ int gn_model_create(gn_model** out, const gn_config* cfg, int device) {
   GN_REQUIRE(m, "out of host memory");
   m->cfg = *cfg;
   m->device = device;
-  m->act_bf16 = cfg->precision == GN_PREC_BF16;
+  m->act_bf16 = cfg->precision == GN_PREC_BF16 || cfg->precision == GN_PREC_FP16;
+  m->fp16 = cfg->precision == GN_PREC_FP16;
   m->force_simt = cfg->precision == GN_PREC_FP32;
   m->tf32 = cfg->precision == GN_PREC_TF32;
-  m->fold = (m->act_bf16 && !cfg->qk_norm && cfg->fold_ln && cfg->d_model % 64 == 0) ? 1 : 0;
+  m->fold = (m->act_bf16 && !m->fp16 && !cfg->qk_norm && cfg->fold_ln && cfg->d_model % 64 == 0) ? 1 : 0;
   {
     const char* e = getenv("GENIE_B200_TEMPORAL_V2");
     const bool on = !(e && (e[0] == '0' || e[0] == 'n' || e[0] == 'N'));
     AttnArgs probe{};
-    probe.act_bf16 = m->act_bf16; probe.n_heads = cfg->num_heads; probe.head_dim = cfg->d_model / cfg->num_heads;
+    probe.act_bf16 = m->act_bf16; probe.fp16 = m->fp16; probe.n_heads = cfg->num_heads; probe.head_dim = cfg->d_model / cfg->num_heads;
     const char* q = getenv("GENIE_B200_QKN_EPI");   // 0: keep qk-LayerNorm inside the (mma.sync) attention kernels
     const bool qon = !(q && (q[0] == '0' || q[0] == 'n' || q[0] == 'N'));
     m->qkn_epi = (qon && cfg->qk_norm && m->act_bf16 && !cfg->generic_attention && probe.head_dim == 64 &&
@@ -765,7 +769,7 @@ int gn_model_set_weight(gn_model* m, const char* key, const float* src, const in
   auto put_mat = [&](void** dst, int64_t n) -> int {
     GN_PROPAGATE(want(n));
     if (!*dst) GN_PROPAGATE(dev_alloc(m, dst, (size_t)n * m->esz()));
-    if (m->act_bf16) GN_PROPAGATE(launch_cast_bf16(src, (bf16*)*dst, n, st));
+    if (m->act_bf16) GN_PROPAGATE(launch_cast_h16(src, *dst, m->fp16, n, st));
     else if (m->tf32) GN_PROPAGATE(launch_round_tf32(src, (float*)*dst, n, st));
     else GN_CUDA_CHECK(cudaMemcpyAsync(*dst, src, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
     m->have.insert(k);
@@ -888,12 +892,12 @@ int gn_attention_forward(gn_model* m, int layer, int which, const float* x, floa
   GN_PROPAGATE(ensure_workspace(m, n));
   const void* ain = x;
   if (bf || m->tf32) {
-    GN_PROPAGATE(launch_prep(x, m->a, bf, nullptr, nullptr, n, d, 1.f, 1, 1, -1, st, m->tf32));
+    GN_PROPAGATE(launch_prep(x, m->a, m->o16(), nullptr, nullptr, n, d, 1.f, 1, 1, -1, st, m->tf32));
     ain = m->a;
   }
   GN_PROPAGATE(linear(m, ain, d, w.qkv_w, d, w.qkv_b, nullptr, m->big, 3 * d, nullptr, n, 3 * d, EPI_STORE, bf, st));
   AttnArgs aa{};
-  aa.qkv = m->big; aa.out = m->o; aa.act_bf16 = bf; aa.n_heads = c.num_heads; aa.head_dim = hd;
+  aa.qkv = m->big; aa.out = m->o; aa.act_bf16 = bf; aa.fp16 = m->fp16; aa.n_heads = c.num_heads; aa.head_dim = hd;
   aa.scale = c.use_mup ? 8.0f / hd : 1.0f / sqrtf((float)hd);
   aa.qk_gamma = w.norm_g; aa.qk_beta = w.norm_b; aa.round_tf32 = m->tf32;
   GN_PROPAGATE(launch_generic_attention(aa, n_seq, n_tok, causal, st));
@@ -1055,6 +1059,8 @@ int gn_spatial_attention(const void* qkv, void* out, int n_frames, int S, int n_
   GN_REQUIRE(qkv && out && n_frames > 0 && S > 0 && n_heads > 0 && head_dim > 0, "gn_spatial_attention: invalid argument");
   AttnArgs aa{};
   aa.qkv = qkv; aa.out = out; aa.act_bf16 = 1; aa.n_heads = n_heads; aa.head_dim = head_dim; aa.scale = scale;
+  aa.fp16 = (kernel & 0x100) ? 1 : 0;   // bit 8: the buffers hold IEEE fp16 instead of bf16
+  kernel &= 0xff;
   cudaStream_t st = (cudaStream_t)stream;
   if (kernel == 1) {
     GN_REQUIRE(fast_spatial_supported(aa, S), "mma.sync spatial kernel does not support this shape");
@@ -1068,7 +1074,9 @@ int gn_linear_forward(const void* a, const void* w, const float* bias, const flo
   LinearArgs la{};
   la.A = a; la.lda = K; la.W = w; la.ldw = K; la.bias = bias; la.resid = resid; la.ldr = N;
   la.out = out; la.ldo = N; la.out2 = out2; la.ldo2 = N;
-  la.M = M; la.N = N; la.K = K; la.epi = epi; la.in_bf16 = in_bf16; la.out_bf16 = out_bf16; la.force_simt = force_simt;
+  la.M = M; la.N = N; la.K = K; la.epi = epi; la.in_bf16 = in_bf16 != 0; la.out_bf16 = out_bf16 != 0;
+  la.fp16 = in_bf16 == 2 || out_bf16 == 2;   // 2 = IEEE fp16 instead of bf16
+  la.force_simt = force_simt;
   return linear_forward(la, (cudaStream_t)stream);
 }
 

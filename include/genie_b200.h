@@ -28,6 +28,9 @@ extern "C" {
 #define GN_PREC_BF16 0 /* tcgen05 kind::f16, bf16 operands+activations, fp32 accumulate/residual/LN/softmax */
 #define GN_PREC_TF32 1 /* tcgen05 kind::tf32, fp32 activations (parity mode, <= 1e-3 rel) */
 #define GN_PREC_FP32 2 /* CUDA-core fp32 FMA everywhere (exactness checks; slow) */
+#define GN_PREC_FP16 3 /* tcgen05 kind::f16 with IEEE fp16 operands+activations (11-bit mantissa = tf32's), fp32
+                          accumulate/residual/LN/softmax: the bf16 kernels at the bf16 speed, logits <= 1e-3 rel
+                          (parity mode of the tensor-core path; conversions saturate at +-65504) */
 
 #define GN_UNMASK_RANDOM 0 /* st_mask_git.py:204-206 (default of the reference) */
 #define GN_UNMASK_GREEDY 1 /* st_mask_git.py:201-203 */
@@ -131,14 +134,16 @@ int gn_forward_loss(gn_model* m, const int32_t* input_ids, const int32_t* labels
                     void* stream);
 
 /* Test hook for the linear layer kernel: out[M,N] = epi(A[M,K] . W[N,K]^T + bias) (+ resid).
- * a/w dtype: in_bf16 ? bf16 : fp32; out dtype: out_bf16 ? bf16 : fp32; epi 0 store / 1 erf-GELU / 2 residual;
- * out2 (nullable) bf16 copy for epi 2; force_simt selects the CUDA-core kernel. */
+ * a/w dtype: in_bf16 0 fp32 / 1 bf16 / 2 fp16; out dtype: out_bf16 0 fp32 / 1 bf16 / 2 fp16 (16-bit in and out share
+ * one format); epi 0 store / 1 erf-GELU / 2 residual; out2 (nullable) 16-bit copy for epi 2; force_simt selects the
+ * CUDA-core kernel. */
 int gn_linear_forward(const void* a, const void* w, const float* bias, const float* resid, void* out, void* out2,
                       int M, int N, int K, int epi, int in_bf16, int out_bf16, int force_simt, void* stream);
 
 /* Test hook for the spatial attention kernels (the attention core of SelfAttention.forward, attention.py:48-58,
  * non-causal): qkv [n_frames*S, 3*d] bf16 (column order (3, h, hd)) -> out [n_frames*S, d] bf16, d = n_heads*head_dim.
- * kernel: 0 = library default (tcgen05 kernel when supported), 1 = mma.sync kernel, 2 = CUDA-core generic kernel. */
+ * kernel: 0 = library default (tcgen05 kernel when supported), 1 = mma.sync kernel, 2 = CUDA-core generic kernel;
+ * + 0x100: the buffers hold IEEE fp16 instead of bf16. */
 int gn_spatial_attention(const void* qkv, void* out, int n_frames, int S, int n_heads, int head_dim, float scale,
                          int kernel, void* stream);
 
@@ -191,6 +196,10 @@ int gn_vq_decode(gn_vq* m, const int32_t* ids, int B, int h, int w, int little_e
 
 /* counters for bench accounting */
 uint64_t gn_kernel_launches(void);              /* kernels launched by this library since load */
+uint64_t gn_fallback_launches(void);            /* of those: launches that left the intended Blackwell kernel for a slower
+                                                   variant because of a shape / alignment cliff (CUDA-core GEMM on a
+                                                   tensor-core handle, mma.sync / generic attention on a 16-bit handle);
+                                                   0 on the production shapes (GENIE_138M, d=1024 h=16), asserted in tests */
 double gn_model_flops_per_clip_forward(gn_model* m); /* dense reference-equivalent FLOPs */
 double gn_model_flops_executed(gn_model* m);    /* FLOPs actually issued by linear+attention kernels since reset */
 void gn_model_reset_counters(gn_model* m);
