@@ -70,6 +70,7 @@ SIGNATURES = {
     "gn_fallback_launches": (C.c_uint64, []),
     "gn_model_flops_per_clip_forward": (C.c_double, [_vp]),
     "gn_model_flops_executed": (C.c_double, [_vp]),
+    "gn_model_bytes_executed": (C.c_double, [_vp]),
     "gn_model_reset_counters": (None, [_vp]),
 }
 

@@ -28,6 +28,9 @@ def parse_args(argv=None):
     p.add_argument("--maskgit_steps", type=int, default=2)
     p.add_argument("--temperature", type=float, default=0)
     p.add_argument("--max_examples", type=int)
+    p.add_argument("--precision", type=str, default="fp16", choices=["fp16", "bf16", "tf32", "fp32"],
+                   help="B200-path extra: operand format of the tensor-core kernels (fp16 = parity mode at full speed, "
+                        "fp32 = CUDA-core exact mode)")
     return p.parse_args(argv)
 
 
@@ -43,7 +46,7 @@ def main(argv=None):
     if args.max_examples is not None:
         ds.valid_start_inds = ds.valid_start_inds[:args.max_examples]
     clips = ds.clips()
-    model = STMaskGIT.from_pretrained(args.checkpoint_dir, kv_cache=True).to(f"cuda:{local}")
+    model = STMaskGIT.from_pretrained(args.checkpoint_dir, kv_cache=True, precision=args.precision).to(f"cuda:{local}")
     t0 = time.time()
     res = evaluate_clips(clips, b200_backend(model, maskgit_steps=args.maskgit_steps, noise_seed=42,
                                               temperature=args.temperature),

@@ -26,6 +26,9 @@ def parse_args(argv=None):
     p.add_argument("--teacher_force_time", action="store_true")
     p.add_argument("--maskgit_steps", type=int, default=2)
     p.add_argument("--temperature", type=float, default=0)
+    p.add_argument("--precision", type=str, default="fp16", choices=["fp16", "bf16", "tf32", "fp32"],
+                   help="B200-path extra: operand format of the tensor-core kernels (fp16 = parity mode at full speed, "
+                        "fp32 = CUDA-core exact mode)")
     return p.parse_args(argv)
 
 
@@ -39,7 +42,7 @@ def main(argv=None):
     ds = RawTokenDataset(args.val_data_dir, window_size=args.window_size, stride=STRIDE)
     s = ds.metadata["s"]
     example = ds[args.example_ind]["input_ids"].reshape(1, args.window_size, s, s)
-    model = STMaskGIT.from_pretrained(args.checkpoint_dir, kv_cache=True).to("cuda")
+    model = STMaskGIT.from_pretrained(args.checkpoint_dir, kv_cache=True, precision=args.precision).to("cuda")
     out = generate_clips(model, example, args.num_prompt_frames, args.maskgit_steps, args.temperature)
     write_reference_format(args.output_dir, example[0], out[0].cpu(), args.num_prompt_frames, ds.metadata, vars(args))
 

@@ -55,5 +55,6 @@ class GenieConfig:
 
     def __post_init__(self):
         self.factored_vocab_size = nth_root(self.image_vocab_size, self.num_factored_vocabs)
-        if self.attn_drop != 0.0 or self.mlp_drop != 0.0:
-            raise NotImplementedError("dropout > 0 is a training-only feature; the B200 path is inference-only")
+        # attn_drop / mlp_drop are accepted and ignored: dropout is the identity in eval mode, and this path is
+        # inference-only (the reference loads such checkpoints for generate.py / evaluate.py too).  Training
+        # (train.py, data.get_maskgit_collator) is out of scope: SURVEY.md section 2 rows 9 and 16.

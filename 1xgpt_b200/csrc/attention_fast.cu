@@ -244,11 +244,8 @@ int launch_spatial_t(const AttnArgs& a, int n_frames, int S, cudaStream_t st) {
   GN_PROPAGATE(make_tensor_map_2d(&tmKV, a.qkv, H16<H>::TMAP, 2, 3 * d, rows, 3 * d, HD, S, sw));
   const int smem = (SP_QROWS + 2 * S) * HD * 2 + 64 + 1024;
   auto kern = spatial_attn_kernel<HD, H>;
-  static int set = 0;
-  if (smem > set) {
-    GN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    set = smem;
-  }
+  static DevSmemOptIn optin;
+  GN_CUDA_CHECK(ensure_smem_optin(optin, kern, smem));
   dim3 grid(S / SP_QROWS, a.n_heads, n_frames);
   GN_CUDA_CHECK(launch_kernel(PC_SPATIAL, kern, grid, dim3(SP_THREADS), (size_t)smem, st, tmQ, tmKV, static_cast<H*>(a.out), S, d,
                               a.scale * 1.4426950408889634f, a.qk_gamma, a.qk_beta));
@@ -442,18 +439,9 @@ int launch_temporal_t(const AttnArgs& a, int B, int S, int T, int t0, int Tq, vo
   const int d = a.n_heads * a.head_dim;
   const int smem = a.n_heads * 2 * 3 * 16 * HD * 2 + 1024;
   auto kern = temporal_attn_kernel<HD, H>;
-  static int set = 0;
-  if (smem > 48 * 1024 && smem > set) {
-    GN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    set = smem;
-  }
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
+  static DevSmemOptIn optin;
+  if (smem > 48 * 1024) GN_CUDA_CHECK(ensure_smem_optin(optin, kern, smem));
+  const int sms = device_sm_count();
   const int per_sm = std::max(1, (227 * 1024) / smem);
   const int n_pos = B * S;
   const int grid = std::min(n_pos, sms * per_sm);
@@ -680,18 +668,9 @@ int launch_temporal_v2(const AttnArgs& a, int nb, int S, int T, int t0, int Tq, 
   GN_REQUIRE(ns >= 2, "temporal attention v2: a stage of %d bytes does not fit twice in shared memory", stage);
   const int smem = ns * stage + 1024 + 2 * ns * 8;
   auto kern = temporal_attn_v2_kernel<E>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
+  static DevSmemOptIn optin;
+  GN_CUDA_CHECK(ensure_smem_optin(optin, kern, 227 * 1024));
+  const int sms = device_sm_count();
   const int grid = std::min(n_pos, sms * per_sm);
   const char* he = getenv("GENIE_B200_KV_HINT");   // 0: plain loads of the K/V cache (A/B measurements)
   const int hint = !(he && he[0] == '0');

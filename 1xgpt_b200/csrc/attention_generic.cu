@@ -150,11 +150,8 @@ int launch_generic_t(const AttnArgs& a, int n_seq, GenericMap mp, int nq, int nk
   const size_t smem = ((size_t)nk * (hd + 1) + (size_t)nk * hd + 4 * (size_t)nk + 4 * (size_t)hd) * sizeof(float);
   GN_REQUIRE(smem <= 227 * 1024, "generic attention: sequence %d x head_dim %d does not fit shared memory", nk, hd);
   auto kern = generic_attention_kernel<T>;
-  static size_t max_set = 0;
-  if (smem > 48 * 1024 && smem > max_set) {
-    GN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    max_set = smem;
-  }
+  static DevSmemOptIn optin;
+  if (smem > 48 * 1024) GN_CUDA_CHECK(ensure_smem_optin(optin, kern, (int)smem));
   dim3 grid(n_seq, a.n_heads);
   kern<<<grid, 128, smem, st>>>(static_cast<const T*>(a.qkv), static_cast<T*>(a.out), static_cast<const T*>(kc_in),
                                 static_cast<const T*>(vc_in), static_cast<T*>(kc_out), static_cast<T*>(vc_out), mp,

@@ -246,11 +246,8 @@ int launch_tc_t(const AttnArgs& a, int n_frames, cudaStream_t st) {
   GN_PROPAGATE(make_tensor_map_2d(&tmO, a.out, H16<H>::TMAP, 2, d, rows, d, TCA_HD, TCA_QROWS, sw));
   const int smem = (TCA_QROWS + 2 * SK) * TCA_ROWB + 64 + 4 * TCA_QROWS * 4 + 1024;
   auto kern = spatial_attn_tc_kernel<SK, H>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  static DevSmemOptIn optin;
+  GN_CUDA_CHECK(ensure_smem_optin(optin, kern, smem));
   dim3 grid(SK / TCA_QROWS, a.n_heads, n_frames);
   GN_CUDA_CHECK(launch_kernel(PC_SPATIAL, kern, grid, dim3(TCA_THREADS), (size_t)smem, st, tmQ, tmKV, tmO, d,
                               a.scale * 1.4426950408889634f));
@@ -519,17 +516,9 @@ int launch_tc_persistent(const AttnArgs& a, int n_frames, cudaStream_t st) {
                                   sw));
   GN_PROPAGATE(make_tensor_map_2d(&tmO, a.out, H16<H>::TMAP, 2, d, rows, d, TCA_HD, TCA_QROWS, sw));
   const int smem = TCP_STAGES * TCP_STAGE_BYTES + (int)sizeof(TcpBars) + 1024;
-  static bool attr_set = false;
-  static int sms = 0;
-  if (!attr_set) {
-    GN_CUDA_CHECK(cudaFuncSetAttribute(spatial_attn_tc_persistent_kernel<H>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-    attr_set = true;
-  }
+  static DevSmemOptIn optin;
+  GN_CUDA_CHECK(ensure_smem_optin(optin, spatial_attn_tc_persistent_kernel<H>, smem));
+  const int sms = device_sm_count();
   const int n_items = n_frames * a.n_heads;
   const int grid = n_items < sms ? n_items : sms;
   GN_CUDA_CHECK(launch_kernel(PC_SPATIAL, spatial_attn_tc_persistent_kernel<H>, dim3(grid), dim3(TCP_THREADS),

@@ -150,6 +150,27 @@ inline cudaError_t launch_kernel_cluster(int cat, void (*kern)(KArgs...), dim3 g
   return e;
 }
 
+// ---- per-device one-time setup.  cudaFuncSetAttribute / cudaDeviceSetLimit and the SM count belong to the device that
+// is current when they are called; the C ABI takes a device index per handle, so every such cache is keyed by the
+// device ordinal (a second handle on another GPU of the same process gets its own opt-ins).
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+int device_sm_count();   // SMs of the current device (runtime.cu)
+struct DevSmemOptIn { int set[kMaxDevices] = {}; };
+// raise the dynamic-shared-memory limit of `kern` on the current device to at least `bytes` (no-op once done)
+template <typename K>
+inline cudaError_t ensure_smem_optin(DevSmemOptIn& s, K kern, int bytes) {
+  const int dev = current_device();
+  if (bytes <= s.set[dev]) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) s.set[dev] = bytes;
+  return e;
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -221,6 +221,7 @@ int launch_fold_ln(const float* W, const float* gamma, const float* beta, const 
                    float* bias_f, int N, int K, cudaStream_t st) {
   fold_ln_kernel<<<ceil_div(N, 8), 256, 0, st>>>(W, gamma, beta, bias, Wf, colsum, bias_f, N, K);
   GN_CUDA_CHECK(cudaGetLastError());
+  ++g_launch_count;
   return GN_OK;
 }
 

@@ -702,21 +702,15 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
     tmV = tmO;
   }
   auto kern = gemm_tcgen05_kernel<InT, BLOCK_N, EPI, OutT, DUAL, CTAS, QKN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
-    attr_set = true;
-  }
+  static DevSmemOptIn optin;
+  GN_CUDA_CHECK(ensure_smem_optin(optin, kern, SM::TOTAL));
   const int num_tiles = ceil_div(a.M, BLOCK_M * CTAS) * (a.N / BLOCK_N);
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  static int cached_sms = 0;
-  if (!cached_sms) cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev);
-  sms = cached_sms > 0 ? cached_sms : 148;
+  const int sms = device_sm_count();
   int grid = num_tiles < sms ? num_tiles : sms;
   if (CTAS == 2) {
     // persistent pairs: as many 2-CTA clusters as can be co-resident (one CTA per SM, both SMs of a TPC)
-    static int max_pairs = 0;
+    static int max_pairs_dev[kMaxDevices] = {};
+    int& max_pairs = max_pairs_dev[current_device()];
     if (!max_pairs) {
       cudaLaunchConfig_t qc{};
       qc.gridDim = dim3(sms);

@@ -38,6 +38,8 @@ struct LayerW {
 
 }  // namespace
 
+static int g_live_handles[gn::kMaxDevices] = {};   // gn_model handles alive per device (persisting-L2 reset at the last one)
+
 struct gn_model {
   gn_config cfg;
   int device = 0;
@@ -111,9 +113,10 @@ struct gn_model {
   int64_t tokens_cap = 0;
 
   double flops_executed = 0.0;
+  double bytes_executed = 0.0;   // algorithmic HBM bytes of the launches (operands + outputs once per launch)
 
   // CUDA graphs of run_layers, keyed by (b0, nb, t0, Tact, use_cache); invalidated when a buffer is reallocated
-  struct GraphEntry { cudaGraphExec_t exec; double flops; unsigned long long launches; };
+  struct GraphEntry { cudaGraphExec_t exec; double flops; double bytes; unsigned long long launches; };
   std::map<std::vector<int>, GraphEntry> graphs;
 
   size_t esz() const { return act_bf16 ? 2 : 4; }
@@ -270,7 +273,19 @@ int linear(gn_model* m, const void* A, int64_t lda, const void* W, int K, const 
   la.a_evict_first = (stream_hint && (A == m->o || A == m->big)) ? 1 : 0;
   la.round_out_tf32 = (m->tf32 && epi == EPI_GELU) ? 1 : 0;
   m->flops_executed += 2.0 * M * (double)N * K;
+  {
+    const double e = (double)m->esz();
+    m->bytes_executed += (double)M * K * e + (double)N * K * e + (double)M * N * (out_bf16 ? 2.0 : 4.0) +
+                         (resid ? (double)M * N * 4.0 : 0.0) + (out2 ? (double)M * N * 2.0 : 0.0);
+  }
   return linear_forward(la, st);
+}
+
+// LayerNorm / cast pass (launch_prep) + its algorithmic bytes: fp32 row in, operand-format row out
+int prep(gn_model* m, const float* gamma, const float* beta, int n, cudaStream_t st, int S, int Tact) {
+  const int d = m->cfg.d_model;
+  m->bytes_executed += (double)n * d * (4.0 + (double)m->esz());
+  return launch_prep(m->x, m->a, m->o16(), gamma, beta, n, d, 1.f, S, Tact, -1, st, m->tf32);
 }
 
 // temporal QKV projection + causal attention over the frames of each spatial position (st_transformer.py:77-78,
@@ -306,6 +321,8 @@ int temporal_block(gn_model* m, int l, const void* ain, AttnArgs aa, int b0, int
     GN_PROPAGATE(launch_temporal_attention(aa, nb, S, T, t0, Tact, kc, vc, c.generic_attention || !bf, st));
   }
   m->flops_executed += 4.0 * (t0 + Tact) * (double)d * n;
+  // Q + output rows, and K/V of frames [0, t0 + Tact) of every (clip, position)
+  m->bytes_executed += (2.0 * n * d + 2.0 * (double)nb * S * (t0 + Tact) * d) * (double)m->esz();
   return GN_OK;
 }
 
@@ -316,10 +333,16 @@ int run_layers_body(gn_model* m, int b0, int nb, int t0, int Tact, bool use_cach
 // L2 set-aside for the residual stream (see common.cuh): sized once per device, window = the chunk's rows of m->x.
 struct L2WindowScope {
   explicit L2WindowScope(const gn_model* m, int64_t n_rows) {
-    static int64_t setaside = -1;   // bytes available for persisting lines (0: unsupported / disabled)
-    static int64_t max_window_bytes = 0;
-    if (setaside < 0) {
+    // per device: bytes available for persisting lines (0: unsupported / disabled, -1: not probed yet)
+    static int64_t setaside_dev[kMaxDevices], max_window_dev[kMaxDevices];
+    static bool probed[kMaxDevices] = {};
+    const int di = current_device();
+    int64_t& setaside = setaside_dev[di];
+    int64_t& max_window_bytes = max_window_dev[di];
+    if (!probed[di]) {
+      probed[di] = true;
       setaside = 0;
+      max_window_bytes = 0;
       // MB of L2 set aside for the residual stream (0 = off).  Measured on B200 (126 MB L2): 48 MB +1.7 % frames/s,
       // 64 MB and more lose (the wide GEMMs then miss on their operands)
       const char* e = getenv("GENIE_B200_L2_PERSIST");
@@ -398,6 +421,7 @@ int run_layers_body(gn_model* m, int b0, int nb, int t0, int Tact, bool use_cach
       aa.qkv = m->big; aa.out = m->o; aa.act_bf16 = 1; aa.fp16 = m->fp16; aa.n_heads = H; aa.head_dim = hd; aa.scale = scale;
       GN_PROPAGATE(launch_spatial_attention(aa, nb * Tact, S, c.generic_attention, st));
       m->flops_executed += 4.0 * S * (double)d * n;
+      m->bytes_executed += 4.0 * n * d * (double)m->esz();
       GN_PROPAGATE(linear(m, m->o, d, w.attn[0].proj_w, d, w.attn[0].proj_b, m->x, m->x, d, m->a, n, d, EPI_RESID, 0, st));
       GN_PROPAGATE(temporal_block(m, l, m->a, aa, b0, nb, t0, Tact, use_cache, st));
       LnFold ps{};
@@ -422,10 +446,10 @@ int run_layers_body(gn_model* m, int b0, int nb, int t0, int Tact, bool use_cach
     // ---------------- spatial attention: x += proj(attn(qkv(norm1(x))))
     const void* ain;
     if (!c.qk_norm) {
-      GN_PROPAGATE(launch_prep(m->x, m->a, m->o16(), w.ln1_g, w.ln1_b, n, d, 1.f, S, Tact, -1, st, tf));
+      GN_PROPAGATE(prep(m, w.ln1_g, w.ln1_b, n, st, S, Tact));
       ain = m->a;
     } else if (cp) {
-      if (!a_is_x) GN_PROPAGATE(launch_prep(m->x, m->a, m->o16(), nullptr, nullptr, n, d, 1.f, S, Tact, -1, st, tf));
+      if (!a_is_x) GN_PROPAGATE(prep(m, nullptr, nullptr, n, st, S, Tact));
       ain = m->a;
     } else {
       ain = m->x;
@@ -438,10 +462,11 @@ int run_layers_body(gn_model* m, int b0, int nb, int t0, int Tact, bool use_cach
     if (!m->qkn_epi) { aa.qk_gamma = w.attn[0].norm_g; aa.qk_beta = w.attn[0].norm_b; }
     GN_PROPAGATE(launch_spatial_attention(aa, nb * Tact, S, c.generic_attention || !bf, st));
     m->flops_executed += 4.0 * S * (double)d * n;
+    m->bytes_executed += 4.0 * n * d * (double)m->esz();   // q, k, v in, o out
     // the temporal QKV GEMM reads the un-normalised stream: emit its bf16 copy from this epilogue
     GN_PROPAGATE(linear(m, m->o, d, w.attn[0].proj_w, d, w.attn[0].proj_b, m->x, m->x, d, bf ? m->a : nullptr, n, d,
                         EPI_RESID, 0, st));
-    if (tf) GN_PROPAGATE(launch_prep(m->x, m->a, 0, nullptr, nullptr, n, d, 1.f, S, Tact, -1, st, 1));
+    if (tf) GN_PROPAGATE(prep(m, nullptr, nullptr, n, st, S, Tact));
     // ---------------- temporal attention (no LayerNorm in front: st_transformer.py:78)
     if (!m->qkn_epi) { aa.qk_gamma = w.attn[1].norm_g; aa.qk_beta = w.attn[1].norm_b; }
     GN_PROPAGATE(temporal_block(m, l, cp ? m->a : (const void*)m->x, aa, b0, nb, t0, Tact, use_cache, st));
@@ -450,10 +475,10 @@ int run_layers_body(gn_model* m, int b0, int nb, int t0, int Tact, bool use_cach
                         d, EPI_RESID, 0, st));
     // ---------------- MLP: x += fc2(gelu(fc1(norm2(x))))
     if (!c.qk_norm) {
-      GN_PROPAGATE(launch_prep(m->x, m->a, m->o16(), w.ln2_g, w.ln2_b, n, d, 1.f, S, Tact, -1, st, tf));
+      GN_PROPAGATE(prep(m, w.ln2_g, w.ln2_b, n, st, S, Tact));
       ain = m->a;
     } else if (cp) {
-      if (tf) GN_PROPAGATE(launch_prep(m->x, m->a, 0, nullptr, nullptr, n, d, 1.f, S, Tact, -1, st, 1));
+      if (tf) GN_PROPAGATE(prep(m, nullptr, nullptr, n, st, S, Tact));
       ain = m->a;
     } else {
       ain = m->x;
@@ -476,7 +501,7 @@ int run_layers_graphed(gn_model* m, int b0, int nb, int t0, int Tact, bool use_c
   const std::vector<int> key = {b0, nb, t0, Tact, use_cache ? 1 : 0, m->lane};
   auto it = m->graphs.find(key);
   if (it == m->graphs.end()) {
-    const double f0 = m->flops_executed;
+    const double f0 = m->flops_executed, y0 = m->bytes_executed;
     const unsigned long long l0 = g_launch_count;
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
       cudaGetLastError();
@@ -490,14 +515,17 @@ int run_layers_graphed(gn_model* m, int b0, int nb, int t0, int Tact, bool use_c
       cudaGetLastError();
       if (rc != GN_OK) return rc;
       m->flops_executed = f0;
+      m->bytes_executed = y0;
       return run_layers(m, b0, nb, t0, Tact, use_cache, st);   // capture not possible here: run eagerly
     }
     gn_model::GraphEntry e{};
     e.flops = m->flops_executed - f0;
+    e.bytes = m->bytes_executed - y0;
     e.launches = g_launch_count - l0;
     const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
     cudaGraphDestroy(graph);
     m->flops_executed = f0;
+    m->bytes_executed = y0;
     g_launch_count = l0;
     if (ie != cudaSuccess) {
       cudaGetLastError();
@@ -507,6 +535,7 @@ int run_layers_graphed(gn_model* m, int b0, int nb, int t0, int Tact, bool use_c
   }
   GN_CUDA_CHECK(cudaGraphLaunch(it->second.exec, st));
   m->flops_executed += it->second.flops;
+  m->bytes_executed += it->second.bytes;
   g_launch_count += it->second.launches;
   return GN_OK;
 }
@@ -724,6 +753,7 @@ int gn_model_create(gn_model** out, const gn_config* cfg, int device) {
   m->hid = (int)(cfg->d_model * cfg->mlp_ratio);
   m->C = cfg->num_factored_vocabs * cfg->factored_vocab_size;
   m->layers.resize(cfg->num_layers);
+  ++g_live_handles[device < kMaxDevices ? device : 0];
   *out = m;
   return GN_OK;
 }
@@ -739,7 +769,9 @@ void gn_model_destroy(gn_model* m) {
   if (m->lane_fork) cudaEventDestroy(m->lane_fork);
   for (void* p : m->owned)
     if (p) cudaFree(p);
-  cudaCtxResetPersistingL2Cache();   // lines of the (now freed) residual stream leave the L2 set-aside
+  // lines of the (now freed) residual stream leave the L2 set-aside - only when no other handle on this device is
+  // alive: the reset evicts EVERY persisting line of the context (other handles' windows, PyTorch kernels' policies)
+  if (--g_live_handles[m->device < kMaxDevices ? m->device : 0] <= 0) cudaCtxResetPersistingL2Cache();
   cudaGetLastError();
   delete m;
 }
@@ -966,6 +998,9 @@ int gn_generate(gn_model* m, int32_t* tokens, int B, int t_prompt, int steps, fl
 int gn_generate_host(gn_model* m, int32_t* tokens_host, int B, int t_prompt, int steps, float temperature,
                      int unmask_mode, const float* noise_host, const float* uniform_host, void* stream) {
   GN_REQUIRE(m && tokens_host && B > 0, "gn_generate_host: invalid argument");
+  // validate before any staging buffer is sized from (steps - 1)
+  GN_PROPAGATE(check_generate_args(m, B, steps, temperature, unmask_mode, noise_host, uniform_host));
+  GN_REQUIRE(t_prompt >= 1 && t_prompt <= m->cfg.T, "num_prompt_frames %d out of range [1, %d]", t_prompt, m->cfg.T);
   DeviceGuard g(m->device);
   cudaStream_t st = (cudaStream_t)stream;
   const gn_config& c = m->cfg;
@@ -1117,8 +1152,9 @@ double gn_model_flops_per_clip_forward(gn_model* m) {
   return (c.num_layers * per_tok_layer + 2.0 * d * m->C) * c.T * c.S;
 }
 double gn_model_flops_executed(gn_model* m) { return m ? m->flops_executed : 0.0; }
+double gn_model_bytes_executed(gn_model* m) { return m ? m->bytes_executed : 0.0; }
 void gn_model_reset_counters(gn_model* m) {
-  if (m) m->flops_executed = 0.0;
+  if (m) m->flops_executed = m->bytes_executed = 0.0;
 }
 
 }  // extern "C"

@@ -61,6 +61,17 @@ int profile_end(double* out) {
   return GN_OK;
 }
 
+int device_sm_count() {
+  static int sms[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!sms[dev]) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    sms[dev] = n > 0 ? n : 148;
+  }
+  return sms[dev];
+}
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

@@ -404,11 +404,8 @@ int launch_out_conv(const bf16* a, const float* w, const float* bias, float* out
                     int C, cudaStream_t st) {
   GN_REQUIRE(C % 32 == 0 && C <= 512, "output conv: C %d unsupported (multiple of 32, <= 512)", C);
   const size_t smem = (size_t)3 * (OC_PIX + 2) * (C * 2 + 16) + (size_t)9 * C * 16 + (size_t)4 * OC_PIX * 3 * 4;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    GN_CUDA_CHECK(cudaFuncSetAttribute(out_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  static DevSmemOptIn optin;
+  GN_CUDA_CHECK(ensure_smem_optin(optin, out_conv_kernel, (int)smem));
   dim3 grid(ceil_div(W, OC_PIX), H, B);
   out_conv_kernel<<<grid, 128, smem, st>>>(a, w, bias, out_f32, out_u8, H, W, C);
   GN_CUDA_CHECK(cudaGetLastError());

@@ -57,6 +57,11 @@ def _stream(device):
 class _Rooted(nn.Module):
     """Sub-modules keep a weak reference to the owning STMaskGIT (which owns the native handle)."""
 
+    def __getstate__(self):          # weakrefs are neither picklable nor deep-copyable; the owner re-links its copy
+        state = dict(self.__dict__)
+        state.pop("_root_ref", None)
+        return state
+
     def _root_model(self) -> "STMaskGIT":
         ref = self.__dict__.get("_root_ref")
         root = ref() if ref is not None else None
@@ -164,7 +169,10 @@ class STMaskGIT(nn.Module):
     """Drop-in for genie/st_mask_git.py:29 STMaskGIT (inference path).
 
     Extra keyword arguments (all optional, reference behaviour by default):
-      precision         "bf16" (tcgen05 kind::f16, default) | "tf32" (parity mode) | "fp32" (CUDA-core, exact)
+      precision         "fp16" (default: tcgen05 kind::f16 with IEEE fp16 operands, fp32 accumulate / residual / LN /
+                        softmax; logits within 1e-3 rel of the reference at full tensor-core speed) | "bf16" (same
+                        kernels, bf16 operands: fp32 range, 5e-3..8e-3 rel) | "tf32" (tcgen05 kind::tf32, fp32
+                        activations) | "fp32" (CUDA-core FMA, temperature-0 ids bit-exact)
       kv_cache          temporal K/V cache + causal frame trimming for maskgit_generate / generate / evaluate:
                         bit-identical tokens, ~8-10x fewer FLOPs (reference recomputes the full window)
       chunk_tokens      tokens per L2-resident work chunk (0 = default 32768)
@@ -178,7 +186,7 @@ class STMaskGIT(nn.Module):
                         default, 1 = single stream); bit-identical results for any value
     """
 
-    def __init__(self, config: GenieConfig, precision: str = "bf16", kv_cache: bool = False, chunk_tokens: int = 0,
+    def __init__(self, config: GenieConfig, precision: str = "fp16", kv_cache: bool = False, chunk_tokens: int = 0,
                  generic_attention: bool = False, fold_ln: bool = False, cuda_graphs: bool = True,
                  lanes: int = 0):
         super().__init__()
@@ -208,12 +216,7 @@ class STMaskGIT(nn.Module):
         self.__dict__["_native"] = None
         self.__dict__["_native_key"] = None
         self.__dict__["_weights_dirty"] = True
-        ref = weakref.ref(self)
-        self.decoder.__dict__["_root_ref"] = ref
-        for i, blk in enumerate(self.decoder.layers):
-            for which, att in enumerate((blk.spatial_attn, blk.temporal_attn)):
-                att.__dict__["_root_ref"] = ref
-                att.__dict__["_where"] = (i, which)
+        self._relink()
         self.requires_grad_(False)
 
     # ------------------------------------------------------------------ native handle management
@@ -226,6 +229,34 @@ class STMaskGIT(nn.Module):
         out = super().load_state_dict(*a, **k)
         self.__dict__["_weights_dirty"] = True
         return out
+
+    # copies own no native handle: a deep-copied / unpickled model builds its own on first use and re-links its
+    # sub-modules to itself (weakrefs are atomic for copy.deepcopy and would keep pointing at the original)
+    def _relink(self):
+        ref = weakref.ref(self)
+        self.decoder.__dict__["_root_ref"] = ref
+        for i, blk in enumerate(self.decoder.layers):
+            for which, att in enumerate((blk.spatial_attn, blk.temporal_attn)):
+                att.__dict__["_root_ref"] = ref
+                att.__dict__["_where"] = (i, which)
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_native"], state["_native_key"], state["_weights_dirty"] = None, None, True
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._relink()
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__getstate__().items():
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        new._relink()
+        return new
 
     def mark_weights_dirty(self):
         """Call after modifying parameters in place; the next forward re-uploads them."""
@@ -275,7 +306,15 @@ class STMaskGIT(nn.Module):
         torch.cuda.current_stream(self.device).synchronize()  # sources may be temporaries
         _lib.check(h.lib.gn_model_check_weights(h.ptr))
 
-    def _ids32(self, t: torch.Tensor) -> torch.Tensor:
+    def _ids32(self, t: torch.Tensor, labels: bool = False) -> torch.Tensor:
+        """int64 / uint32 ids of the reference -> int32 on the model's device, range-checked on the ORIGINAL dtype:
+        the reference raises an IndexError for ids outside the embedding tables (factorization_utils.py:39-52) or
+        the logit rows (labels); the kernels index with id % V and id / V and must never see such an id."""
+        if t.numel():
+            lo, hi = int(t.min()), int(t.max())
+            top = self.config.image_vocab_size - (1 if labels else 0)      # inputs may hold the mask id
+            if lo < 0 or hi > top:
+                raise IndexError(f"token id out of range: min {lo}, max {hi}, expected [0, {top}]")
         return t.to(device=self.device, dtype=torch.int32).contiguous()
 
     # ------------------------------------------------------------------ module-level seams
@@ -424,7 +463,7 @@ class STMaskGIT(nn.Module):
         c = self.config
         B = input_ids.size(0)
         ids = self._ids32(input_ids.reshape(B, c.T, c.S))
-        lab = self._ids32(labels.reshape(B, c.T, c.S))
+        lab = self._ids32(labels.reshape(B, c.T, c.S), labels=True)
         Cc = c.factored_vocab_size * c.num_factored_vocabs
         logits = torch.empty(B, Cc, c.T, self.h, self.w, device=self.device, dtype=torch.float32)
         acc = torch.zeros(4, device=self.device, dtype=torch.float64)
@@ -443,7 +482,7 @@ class STMaskGIT(nn.Module):
         h = self._handle()
         c = self.config
         B = input_ids.size(0)
-        gt = self._ids32(input_ids.reshape(B, c.T, c.S))
+        gt = self._ids32(input_ids.reshape(B, c.T, c.S), labels=True)
         mode = self._unmask_mode(unmask_mode)
         nz = None
         if mode == _lib.GN_UNMASK_RANDOM and maskgit_steps > 1:
@@ -465,6 +504,10 @@ class STMaskGIT(nn.Module):
     def flops_executed(self) -> float:
         h = self._handle()
         return float(h.lib.gn_model_flops_executed(h.ptr))
+
+    def bytes_executed(self) -> float:
+        h = self._handle()
+        return float(h.lib.gn_model_bytes_executed(h.ptr))
 
     def reset_counters(self):
         h = self._handle()

@@ -202,6 +202,9 @@ uint64_t gn_fallback_launches(void);            /* of those: launches that left 
                                                    0 on the production shapes (GENIE_138M, d=1024 h=16), asserted in tests */
 double gn_model_flops_per_clip_forward(gn_model* m); /* dense reference-equivalent FLOPs */
 double gn_model_flops_executed(gn_model* m);    /* FLOPs actually issued by linear+attention kernels since reset */
+double gn_model_bytes_executed(gn_model* m);    /* algorithmic HBM bytes of those launches since reset: every operand and
+                                                   output of a launch once (GEMM A + W + out + residual, attention
+                                                   q/k/v/o + temporal K/V cache rows, LayerNorm rows in + out) */
 void gn_model_reset_counters(gn_model* m);
 
 #ifdef __cplusplus

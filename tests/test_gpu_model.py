@@ -1,12 +1,15 @@
 """GPU parity of the whole path (through the nn.Module mirror -> C ABI) against the golden fixtures that
 the reference itself produced (tests/golden/*.npz) and against the CPU oracle run live.
 
-Tolerances (rel = Frobenius-relative error of logits):
-  fp32 mode  (CUDA-core FMA)          rel <= 2e-5, temperature-0 token ids bit-exact
-  tf32 mode  (tcgen05 kind::tf32)     rel <= 1e-3   (the north-star bar)
-  bf16 mode  (tcgen05 kind::f16)      rel <= 2e-2   (the reference's own bf16-vs-fp32 gap is 3e-3..1e-2,
-                                                     SURVEY.md section 7.3-1); argmax ids must agree wherever
-                                                     the oracle's top-2 margin exceeds twice the max abs error
+Tolerances (rel = Frobenius-relative error of logits against the reference's fp32 outputs):
+  fp32 mode  (CUDA-core FMA)              rel <= 2e-5, temperature-0 token ids bit-exact
+  fp16 mode  (tcgen05 kind::f16, fp16)    rel <= 1e-3 = the north-star bar (default mode, the one bench.py measures)
+  tf32 mode  (tcgen05 kind::tf32)         rel <= 1e-3
+  bf16 mode  (tcgen05 kind::f16, bf16)    1.5 x the value measured per fixture (MEASURED below); the reference's own
+                                          bf16-vs-fp32 gap is 3e-3..1e-2: no bf16 path meets 1e-3
+In every mode the step-0 argmax ids must equal the reference's wherever the reference's top-2 margin exceeds 4x the
+measured max abs logit error ("solid" positions), and the final-token agreement may not fall below the measured
+value by more than half of its distance to 1.
 """
 import importlib
 
@@ -19,11 +22,34 @@ from helpers import O, build_b200_model, golden_cfg, golden_sd, load_golden, rel
 pytestmark = pytest.mark.gpu
 
 TINY = ["tiny_preln", "tiny_qknorm_mup", "tiny_qknorm"]
-TOL = {"fp32": 2e-5, "tf32": 1e-3, "bf16": 2e-2}
+BAR = 1e-3                         # north star: logits within 1e-3 rel of the reference forward
+TOL = {"fp32": 2e-5, "tf32": BAR, "fp16": BAR, "bf16": 2e-2}
+# measured on B200 (profiles/r02_parity.jsonl, scripts/parity_report.py): (fixture, mode) -> (logits rel, final-token
+# agreement of MaskGIT-2 at frame 8)
+MEASURED = {
+    ("genie35m", "fp16"): (8.43e-4, 0.9707), ("genie138m", "fp16"): (8.49e-4, 1.0),
+    ("genie138m_qknorm_mup", "fp16"): (7.11e-4, 0.9961),
+    ("genie35m", "tf32"): (8.30e-4, 0.9922), ("genie138m", "tf32"): (8.28e-4, 1.0),
+    ("genie138m_qknorm_mup", "tf32"): (7.22e-4, 1.0),
+    ("genie35m", "bf16"): (7.64e-3, 0.9082), ("genie138m", "bf16"): (6.47e-3, 0.9922),
+    ("genie138m_qknorm_mup", "bf16"): (5.44e-3, 1.0),
+}
+
+
+def logits_tol(name, precision):
+    if precision == "fp32":
+        return TOL["fp32"]
+    t = 1.5 * MEASURED[(name, precision)][0]
+    return min(t, BAR) if precision in ("fp16", "tf32") else t
+
+
+def agreement_floor(name, precision):
+    a = MEASURED[(name, precision)][1]
+    return min(a - 0.5 * (1.0 - a), 0.99)
 
 
 @pytest.mark.parametrize("name", TINY)
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "fp16", "bf16"])
 def test_tiny_logits_match_reference(name, precision):
     z = load_golden(name)
     kw, sd = golden_cfg(z), golden_sd(z)
@@ -101,7 +127,7 @@ def _prod_setup(name):
 
 
 @pytest.mark.parametrize("name", PROD)
-@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+@pytest.mark.parametrize("precision", ["fp16", "bf16", "tf32"])
 def test_production_logits_match_reference(name, precision):
     z, kw, cfg, sd = _prod_setup(name)
     m = build_b200_model(kw, sd, precision=precision)
@@ -113,8 +139,8 @@ def test_production_logits_match_reference(name, precision):
     err = rel_fro(sub, ref)
     fro = float(torch.linalg.vector_norm(logits.double()))
     print(f"{name} {precision}: rel(sub) {err:.3e}  fro {fro:.6e} vs ref {float(z['logits_full_fro']):.6e}")
-    assert err < TOL[precision]
-    assert abs(fro - float(z["logits_full_fro"])) / float(z["logits_full_fro"]) < TOL[precision]
+    assert err < logits_tol(name, precision)
+    assert abs(fro - float(z["logits_full_fro"])) / float(z["logits_full_fro"]) < logits_tol(name, precision)
 
 
 @pytest.mark.parametrize("name", PROD)
@@ -130,7 +156,8 @@ def test_production_maskgit_argmax_and_tokens(name):
     margin = torch.from_numpy(z["margin0"])                  # [B, NV, S]
     l0_sub_ref = torch.from_numpy(z["logits0_sub"])          # [B, V, NV, 4]
     results = {}
-    for precision, kv in [("bf16", False), ("bf16", True), ("fp32", False)]:
+    for precision, kv in [("fp16", False), ("fp16", True), ("bf16", False), ("bf16", True), ("tf32", True),
+                          ("fp32", False)]:
         m = build_b200_model(kw, sd, precision=precision, kv_cache=kv)
         p = prompt0.clone().cuda()
         samples, fl = m.maskgit_generate(p, 8, maskgit_steps=2, temperature=0.0, noise=noise)
@@ -150,10 +177,11 @@ def test_production_maskgit_argmax_and_tokens(name):
             assert torch.equal(samples.reshape(B, -1).cpu(), ref_samples)     # bit-exact ids in the exact mode
             assert torch.equal(p.cpu().reshape(B, -1), torch.from_numpy(z["prompt_after"]).long().reshape(B, -1))
         else:
-            assert tok_equal > 0.85
+            assert tok_equal >= agreement_floor(name, precision)
     # the K/V-cached, frame-trimmed path must reproduce the dense path bit for bit
-    assert torch.equal(results[("bf16", False)][0], results[("bf16", True)][0])
-    assert torch.equal(results[("bf16", False)][1], results[("bf16", True)][1])
+    for precision in ("fp16", "bf16"):
+        assert torch.equal(results[(precision, False)][0], results[(precision, True)][0])
+        assert torch.equal(results[(precision, False)][1], results[(precision, True)][1])
 
 
 def test_fast_vs_generic_attention_kernels():
@@ -243,11 +271,16 @@ def test_wide_model_shapes_d1024_h16(qk_norm, use_mup):
     ids = O.synthetic_clips(cfg, 1, seed=42)
     ids[:, 12:] = cfg.mask_token_id
     ref = O.compute_logits(sd, cfg, ids)
-    for precision in ("bf16", "tf32"):
+    lib = importlib.import_module("1xgpt_b200")._lib.load()
+    measured_bf16 = {False: 5.30e-3, True: 1.73e-3}           # B200, round 1 (gpurun_out/e1_model.log)
+    for precision in ("fp16", "bf16", "tf32"):
         m = build_b200_model(kw, sd, precision=precision)
+        f0 = lib.gn_fallback_launches()
         err = rel_fro(m.compute_logits(ids.cuda()), ref)
         print(f"d1024 h16 qk_norm={qk_norm} {precision}: rel {err:.3e}")
-        assert err < TOL[precision]
+        assert err < (1.5 * measured_bf16[qk_norm] if precision == "bf16" else BAR)
+        if precision != "tf32":
+            assert lib.gn_fallback_launches() == f0    # every launch is the tcgen05 / TMA kernel at this shape
     # 8-step MaskGIT through the cached path == dense path (bit-identical tokens)
     noise = O.tie_free_noise(8, 1, cfg.S, seed=43)
     outs = []
@@ -257,6 +290,81 @@ def test_wide_model_shapes_d1024_h16(qk_norm, use_mup):
         s, _ = m.maskgit_generate(p, 12, maskgit_steps=8, temperature=0.0, noise=noise)
         outs.append(s.cpu())
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "tf32", "bf16"])
+def test_production_forward_loss_35m_config0(precision):
+    """BASELINE.json configs[0]: STMaskGIT.forward (st_mask_git.py:267-279) of genie/configs/magvit_n32_h8_d256.json on
+    2 clips -> loss / acc over the masked positions, against the reference's own numbers (genie35m_fwd.npz)."""
+    z, kw, cfg, sd = _prod_setup("genie35m_fwd")
+    m = build_b200_model(kw, sd, precision=precision)
+    ids = torch.from_numpy(z["ids"]).long()
+    out = m(torch.from_numpy(z["fwd_in"]).long().cuda(), ids.reshape(2, -1).cuda())
+    dl, da = abs(float(out.loss) - float(z["fwd_loss"])), abs(float(out.acc) - float(z["fwd_acc"]))
+    sub = out.logits.reshape(2, -1, cfg.T, cfg.S)[:, :, z["sub_t"].tolist()][:, :, :, z["sub_s"].tolist()]
+    err = rel_fro(sub, torch.from_numpy(z["logits_sub"]))
+    print(f"35M forward {precision}: loss {float(out.loss):.6f} (ref {float(z['fwd_loss']):.6f}, |d| {dl:.2e}), "
+          f"acc |d| {da:.2e}, logits rel {err:.3e}")
+    # measured |d loss|: fp32 <1e-6, fp16 / tf32 ~1e-5, bf16 ~1e-4 (CE averages 12k positions)
+    assert dl < {"fp32": 2e-5, "fp16": 1e-4, "tf32": 1e-4, "bf16": 1e-3}[precision]
+    assert da < (1e-9 if precision == "fp32" else 1e-3)
+    assert err < (TOL["fp32"] if precision == "fp32" else BAR if precision != "bf16" else 1.2e-2)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "tf32", "bf16"])
+def test_production_teacher_forced_eval_138m(precision):
+    """evaluate.py:82-122,173-179 at the GENIE_138M shape, 2 clips, all 15 timesteps, MaskGIT-2, against the numbers
+    the reference produced (genie138m_eval.npz): CE, accuracy, every sampled token."""
+    parity = importlib.import_module("1xgpt_b200.parity")
+    r = parity.eval_parity(precision, kv_cache=True)
+    print(r)
+    assert r["tokens"] == 2 * 15 * 256
+    if precision == "fp32":
+        assert r["ce_abs_diff"] < 2e-5 and r["token_agreement"] == 1.0 and r["acc"] == r["acc_ref"]
+    else:
+        # measured: see EVAL_MEASURED (1.5 x)
+        ce_m, agree_m = EVAL_MEASURED[precision]
+        assert r["ce_abs_diff"] < 1.5 * ce_m
+        assert r["token_agreement"] >= min(agree_m - 0.5 * (1 - agree_m), 0.99)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "tf32", "bf16"])
+def test_production_generate_8_frames_138m(precision):
+    """generate.py:77-103 at the GENIE_138M shape: 8 prompt frames -> 8 generated frames, MaskGIT-2, temperature 0,
+    against the tokens the reference's STMaskGIT.generate produced (genie138m_gen8.npz).  fp32: every id equal.
+    Reduced precision: the first generated frame's solid argmax positions equal; later frames are conditioned on
+    earlier samples, so a single flipped near-tie token changes everything after it - agreement is reported."""
+    parity = importlib.import_module("1xgpt_b200.parity")
+    r = parity.gen8_parity(precision, kv_cache=True)
+    print(r)
+    assert r["first_frame_solid_argmax_mismatches"] == 0
+    if precision == "fp32":
+        assert r["tokens_equal"]
+    else:
+        assert r["token_agreement_first_frame"] >= GEN8_FIRST_FRAME_FLOOR[precision]
+
+
+# measured on B200 (profiles/r02_parity.jsonl): mode -> (|CE - CE_ref|, sampled-token agreement)
+EVAL_MEASURED = {"fp16": (1.85e-4, 0.99909), "tf32": (1.90e-4, 0.99883), "bf16": (7.84e-4, 0.98906)}
+# first generated frame of the 8-frame generate: measured agreement 1.0 / 1.0 / 0.9883
+GEN8_FIRST_FRAME_FLOOR = {"fp16": 0.99, "tf32": 0.99, "bf16": 0.98}
+
+
+def test_no_fallback_launches_on_production_shapes():
+    """GENIE_138M (both flag sets): every launch of a cached generate step is the intended Blackwell kernel - no
+    CUDA-core GEMM, no mma.sync / generic attention (gn_fallback_launches stays constant)."""
+    lib = importlib.import_module("1xgpt_b200")._lib.load()
+    for name in ("genie138m", "genie138m_qknorm_mup"):
+        z, kw, cfg, sd = _prod_setup(name)
+        ids = torch.from_numpy(z["ids"]).long()
+        for precision in ("fp16", "bf16"):
+            m = build_b200_model(kw, sd, precision=precision, kv_cache=True)
+            m.compute_logits(ids.cuda())                       # uploads weights, dense forward
+            f0 = lib.gn_fallback_launches()
+            m.generate(ids[:, :8].reshape(1, -1).cuda(), None, max_new_tokens=8 * cfg.S, maskgit_steps=2,
+                       noise=torch.rand(8, 1, 1, cfg.S))
+            m.compute_logits(ids.cuda())
+            assert lib.gn_fallback_launches() == f0, (name, precision)
 
 
 def test_production_teacher_forced_ce_parity_35m():
@@ -416,3 +524,24 @@ def test_chunk_larger_than_l2_policy_window():
     a = build_b200_model(kw, sd, precision="bf16", chunk_tokens=131072).compute_logits(ids.cuda())
     b = build_b200_model(kw, sd, precision="bf16").compute_logits(ids.cuda())
     assert torch.equal(a.cpu(), b.cpu())
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_devices_in_one_process():
+    """round-1 advisor finding: per-device setup (shared-memory opt-ins, SM count, L2 set-aside) used to be cached
+    process-wide, so a second handle on another GPU launched > 48 KB kernels without the opt-in.  One process, one
+    handle per device: identical logits, bit for bit."""
+    g = importlib.import_module("1xgpt_b200")
+    z, kw, cfg, sd = _prod_setup("genie35m")
+    ids = torch.from_numpy(z["ids"]).long()
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        m = g.STMaskGIT(g.GenieConfig(**kw), precision="fp16", kv_cache=True)
+        m.load_state_dict(sd)
+        m = m.to(dev)
+        outs.append(m.compute_logits(ids.to(dev)).cpu())
+        p = ids.clone()
+        p[:, 8:] = cfg.mask_token_id
+        s, _ = m.maskgit_generate(p.to(dev), 8, maskgit_steps=2, noise=torch.from_numpy(z["noise"]))
+        outs.append(s.cpu())
+    assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3])

@@ -144,3 +144,31 @@ def test_synthetic_state_dict_equals_oracle_generator(kw):
     assert list(a.keys()) == list(b.keys())
     for k in a:
         assert torch.equal(a[k], b[k]), k
+
+
+def test_copies_own_their_submodules_and_ids_are_range_checked():
+    """round-1 advisor findings: deep copies / pickles of STMaskGIT must not route sub-module forwards to the
+    original's handle; ids outside the tables raise like the reference's embedding lookup; dropout configs load."""
+    import copy
+    import pickle
+    cfg = pkg.GenieConfig(num_layers=2, num_heads=4, d_model=64, T=4, S=16, num_factored_vocabs=2, attn_drop=0.1,
+                          mlp_drop=0.2)                     # dropout is accepted (identity at inference)
+    m = pkg.STMaskGIT(cfg)
+    m.init_weights()
+    for clone in (copy.deepcopy(m), pickle.loads(pickle.dumps(m))):
+        assert clone.decoder._root_model() is clone
+        att = clone.decoder.layers[1].temporal_attn
+        assert att._root_model() is clone and att.__dict__["_where"] == (1, 1)
+        assert clone.__dict__["_native"] is None and clone.__dict__["_weights_dirty"]
+        for a, b in zip(m.state_dict().values(), clone.state_dict().values()):
+            assert torch.equal(a, b)
+    assert m.decoder._root_model() is m
+    with pytest.raises(IndexError):
+        m._ids32(torch.tensor([[-1]]))
+    with pytest.raises(IndexError):
+        m._ids32(torch.tensor([[cfg.image_vocab_size + 1]]))
+    with pytest.raises(IndexError):
+        m._ids32(torch.tensor([[cfg.image_vocab_size]]), labels=True)       # the mask id is not a label
+    with pytest.raises(IndexError):
+        m._ids32(torch.tensor([[2 ** 31 + 5]], dtype=torch.int64))            # would wrap negative in int32
+    assert m._ids32(torch.tensor([[cfg.image_vocab_size]])).dtype == torch.int32
