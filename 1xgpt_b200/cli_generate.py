@@ -9,7 +9,7 @@ import argparse
 import torch
 
 from .data import RawTokenDataset
-from .generate import generate_clips, write_reference_format
+from .generate import generate_and_decode, generate_clips, write_reference_format
 from .model import STMaskGIT
 
 STRIDE = 15
@@ -26,6 +26,10 @@ def parse_args(argv=None):
     p.add_argument("--teacher_force_time", action="store_true")
     p.add_argument("--maskgit_steps", type=int, default=2)
     p.add_argument("--temperature", type=float, default=0)
+    p.add_argument("--tokenizer_ckpt", type=str, default=None,
+                   help="B200-path extra: a MAGVIT2 Lightning checkpoint (data/magvit2.ckpt); the generated frames are "
+                        "decoded on the GPU right after sampling and written to <output_dir>/frames_u8.bin "
+                        "(uint8 [new_frames, 3, 16s, 16s])")
     p.add_argument("--precision", type=str, default="fp16", choices=["fp16", "bf16", "tf32", "fp32"],
                    help="B200-path extra: operand format of the tensor-core kernels (fp16 = parity mode at full speed, "
                         "fp32 = CUDA-core exact mode)")
@@ -43,8 +47,16 @@ def main(argv=None):
     s = ds.metadata["s"]
     example = ds[args.example_ind]["input_ids"].reshape(1, args.window_size, s, s)
     model = STMaskGIT.from_pretrained(args.checkpoint_dir, kv_cache=True, precision=args.precision).to("cuda")
-    out = generate_clips(model, example, args.num_prompt_frames, args.maskgit_steps, args.temperature)
+    if args.tokenizer_ckpt:
+        from .vq import VQModel
+        tok = VQModel.from_ckpt(args.tokenizer_ckpt).to("cuda")
+        out, imgs = generate_and_decode(model, tok, example, args.num_prompt_frames, args.maskgit_steps, args.temperature)
+    else:
+        out, imgs = generate_clips(model, example, args.num_prompt_frames, args.maskgit_steps, args.temperature), None
     write_reference_format(args.output_dir, example[0], out[0].cpu(), args.num_prompt_frames, ds.metadata, vars(args))
+    if imgs is not None:
+        import os
+        imgs[0].cpu().numpy().tofile(os.path.join(args.output_dir, "frames_u8.bin"))
 
 
 if __name__ == "__main__":

@@ -27,6 +27,29 @@ def generate_clips(model, clips_THW: torch.Tensor, num_prompt_frames: int = 8, m
     return out.reshape(B, T, H, W)
 
 
+@torch.no_grad()
+def generate_and_decode(model, tokenizer, clips_THW: torch.Tensor, num_prompt_frames: int = 8, maskgit_steps: int = 2,
+                        temperature: float = 0.0, noise: Optional[torch.Tensor] = None, frames: str = "generated",
+                        decode_batch: int = 64):
+    """Sampling fused with the MAGVIT2 decode (visualize.py:104-120 + eval_utils.py:28-41 without the
+    CPU / PIL round trip): gn_generate and gn_vq_decode are enqueued back to back on the current stream of the model's
+    device, the tokens never leave the GPU between them and the frames come back as uint8 on the device.
+
+    clips_THW [B,T,H,W]; `tokenizer` is a 1xgpt_b200.VQModel on the same device.  frames = "generated" decodes the
+    T - num_prompt_frames new frames, "all" the whole window.
+    -> (tokens [B,T,H,W] int64, images uint8 [B, n_frames, 3, 16H, 16W])   (dataset tokens are little-endian)."""
+    if tokenizer.device != model.device:
+        raise ValueError(f"tokenizer on {tokenizer.device}, model on {model.device}: both must share one GPU / stream")
+    out = generate_clips(model, clips_THW, num_prompt_frames, maskgit_steps, temperature, noise)     # [B,T,H,W] on GPU
+    B, T, H, W = out.shape
+    t0 = 0 if frames == "all" else num_prompt_frames
+    flat = out[:, t0:].reshape(-1, H, W)
+    imgs = [tokenizer.decode_tokens(flat[s:s + decode_batch], little_endian=True, as_uint8=True)
+            for s in range(0, flat.shape[0], decode_batch)]
+    imgs = torch.cat(imgs) if len(imgs) > 1 else imgs[0]
+    return out, imgs.reshape(B, T - t0, *imgs.shape[1:])
+
+
 def write_reference_format(output_dir, example_THW: torch.Tensor, generated_THW: torch.Tensor, num_prompt_frames: int,
                            metadata: dict, extra_args: Optional[dict] = None):
     """generate.py:97-116: outputs = [prompt frames, predicted frames, ground-truth frames] of ONE example,

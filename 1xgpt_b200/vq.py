@@ -168,6 +168,39 @@ class VQModel(nn.Module):
             d["_dirty"] = False
         return d["_native"]
 
+    # ------------------------------------------------------------------ checkpoint I/O
+    def init_from_ckpt(self, path, stage: Optional[str] = None):
+        """magvit2/models/lfqgan.py:85-119 for inference: `path` is a Lightning checkpoint ({"state_dict": ...}) of the
+        reference's VQModel.  Its state dict holds the generator (`encoder.*`, `decoder.*`), the GAN / perceptual loss
+        (`loss.*`, dropped), nothing for the LFQ quantizer (all its buffers are non-persistent), and the EMA shadow
+        weights as buffers `model_ema.<parameter name with the dots removed>` (ema.py:20-26).
+          stage=None           the reference's `decode_latents_wrapper` path (visualize.py:100-101): plain resume.  The
+                               reference constructs its LitEma AFTER loading (lfqgan.py:56-57), so the `model_ema.*`
+                               keys of the file are ignored and the live `encoder.* / decoder.*` weights are used.
+          stage="transformer"  the EMA generator weights are loaded instead (lfqgan.py:91-110)."""
+        sd = torch.load(path, map_location="cpu", weights_only=False)
+        sd = sd["state_dict"] if "state_dict" in sd else sd
+        own = self.state_dict()
+        new = {}
+        if stage == "transformer":
+            ema = {k[len("model_ema."):]: v for k, v in sd.items() if k.startswith("model_ema.")}
+            for k in own:
+                s_name = k.replace(".", "")
+                if s_name not in ema:
+                    raise KeyError(f"checkpoint has no EMA weight model_ema.{s_name} for {k}")
+                new[k] = ema[s_name]
+        else:
+            for k in own:
+                if k not in sd:
+                    raise KeyError(f"checkpoint is missing {k}")
+                new[k] = sd[k]
+        self.load_state_dict(new, strict=True)
+        return self
+
+    @classmethod
+    def from_ckpt(cls, path, config: Optional[VQConfig] = None, stage: Optional[str] = None) -> "VQModel":
+        return cls(config).init_from_ckpt(path, stage=stage)
+
     # ------------------------------------------------------------------ API
     @torch.no_grad()
     def encode_to_tokens(self, x: torch.Tensor, return_latents: bool = False):
@@ -213,8 +246,14 @@ class VQModel(nn.Module):
         return self.decode_tokens(ids, little_endian=False)
 
 
-def decode_latents_wrapper(model: VQModel, batch_size: int = 16):
-    """visualize.py:95-122 without PIL: video_data (b,h,w) integer tokens -> uint8 tensor [b,3,H,W] on the host."""
+def decode_latents_wrapper(model=None, batch_size: int = 16, tokenizer_ckpt: Optional[str] = None, device="cuda"):
+    """visualize.py:95-122 without PIL: video_data (b,h,w) integer tokens -> uint8 tensor [b,3,H,W] on the host.
+    Either pass a VQModel, or `tokenizer_ckpt=` (the reference's signature: a Lightning `magvit2.ckpt`)."""
+    if model is None or isinstance(model, (str, bytes)):
+        path = tokenizer_ckpt if model is None else model
+        if path is None:
+            raise ValueError("decode_latents_wrapper needs a VQModel or tokenizer_ckpt=")
+        model = VQModel.from_ckpt(path).to(device)
 
     @torch.no_grad()
     def decode_latents(video_data) -> torch.Tensor:

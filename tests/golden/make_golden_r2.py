@@ -190,8 +190,43 @@ def ckpt_tiny():
     print("ckpt_tiny ok", loss, acc, len(starts), len(kept))
 
 
+def magvit_ckpt():
+    """A Lightning-format MAGVIT2 checkpoint ({"state_dict": ...}) with the key layout the reference's VQModel produces
+    (lfqgan.py:21-119): generator keys `encoder.*` / `decoder.*`, EMA shadow buffers `model_ema.<name without dots>`
+    written by the REFERENCE's LitEma (ema.py:20-26) + its decay / num_updates, and loss / discriminator keys that an
+    inference loader must drop.  Tiny VQConfig so the file stays ~1 MB."""
+    sys.path.insert(0, "/root/reference")
+    from magvit2.config import VQConfig
+    from magvit2.modules.diffusionmodules.improved_model import Encoder, Decoder
+    from magvit2.modules.ema import LitEma
+    torch.manual_seed(71)
+    vq = VQConfig(base_channels=32, ch_mult=(1, 1), num_res_blocks=1)
+
+    class Gen(torch.nn.Module):          # the parameter-holding part of lfqgan.VQModel (LFQ has no persistent state)
+        def __init__(self):
+            super().__init__()
+            self.encoder, self.decoder = Encoder(vq), Decoder(vq)
+            self.loss = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.Conv2d(8, 1, 3))   # stands for loss.*
+
+    g = Gen()
+    ema = LitEma(g)
+    with torch.no_grad():
+        for name, buf in ema.named_buffers():
+            if buf.dtype.is_floating_point and buf.dim() > 0:
+                buf.mul_(0.5).add_(0.01)          # EMA weights differ from the live ones
+    sd = dict(g.state_dict())
+    sd.update({"model_ema." + k: v for k, v in ema.state_dict().items()})
+    torch.save({"state_dict": sd, "epoch": 3, "global_step": 100}, os.path.join(OUT, "magvit_tiny.ckpt"))
+    with open(os.path.join(OUT, "magvit_tiny_keys.json"), "w") as f:
+        json.dump({"keys": sorted(sd), "ema_map": ema.m_name2s_name,
+                   "config": {"base_channels": 32, "ch_mult": [1, 1], "num_res_blocks": 1}}, f)
+    print("magvit_tiny.ckpt ok", len(sd))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["fwd35", "ckpt", "gen8", "eval138"]
+    which = sys.argv[1:] or ["fwd35", "ckpt", "gen8", "eval138", "magvit_ckpt"]
+    if "magvit_ckpt" in which:
+        magvit_ckpt()
     if "fwd35" in which:
         fwd_35m()
     if "ckpt" in which:

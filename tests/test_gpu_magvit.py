@@ -76,3 +76,33 @@ def test_roundtrip_and_batching(setup):
     dec = pkg.decode_latents_wrapper(m, batch_size=4)
     frames = dec(ids.cpu().numpy())
     assert frames.shape == (11, 3, 256, 256) and frames.dtype == torch.uint8
+
+
+def test_generate_and_decode_pipeline(setup):
+    """gn_generate -> gn_vq_decode chained on one stream (tokens stay on the GPU, frames come back as
+    uint8 on the device).  The frames equal a separate decode of the same tokens bit for bit, the tokens equal a plain
+    generate() with the same noise, and the prompt frames decode to the dataset-convention (little-endian) images."""
+    pkg, z, cfg, sd, m = setup
+    gen = importlib.import_module("1xgpt_b200.generate")
+    from helpers import O
+    kw = dict(num_layers=2, num_heads=2, d_model=128, T=16, S=256, image_vocab_size=262144, num_factored_vocabs=2,
+              qk_norm=False, use_mup=False)
+    ocfg = O.OracleConfig(**kw)
+    model = pkg.STMaskGIT(pkg.GenieConfig(**kw), kv_cache=True)
+    model.load_state_dict(O.init_state_dict(ocfg, seed=7, bias_std=0.02))
+    model = model.to("cuda")
+    clips = O.synthetic_clips(ocfg, 3, seed=19)
+    noise = torch.stack([O.tie_free_noise(2, 3, 256, seed=50 + i) for i in range(8)])
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        toks, imgs = gen.generate_and_decode(model, m, clips, 8, 2, 0.0, noise=noise)
+        side.synchronize()
+    assert toks.shape == (3, 16, 16, 16) and imgs.shape == (3, 8, 3, 256, 256) and imgs.dtype == torch.uint8
+    assert imgs.is_cuda and toks.is_cuda
+    assert torch.equal(toks[:, :8].cpu(), clips[:, :8])
+    plain = gen.generate_clips(model, clips, 8, 2, 0.0, noise=noise)
+    assert torch.equal(plain, toks)
+    again = m.decode_tokens(toks[:, 8:].reshape(-1, 16, 16), little_endian=True, as_uint8=True)
+    assert torch.equal(again.reshape(3, 8, 3, 256, 256), imgs)
+    _, allf = gen.generate_and_decode(model, m, clips, 8, 2, 0.0, noise=noise, frames="all", decode_batch=5)
+    assert allf.shape == (3, 16, 3, 256, 256) and torch.equal(allf[:, 8:], imgs)

@@ -172,3 +172,29 @@ def test_copies_own_their_submodules_and_ids_are_range_checked():
     with pytest.raises(IndexError):
         m._ids32(torch.tensor([[2 ** 31 + 5]], dtype=torch.int64))            # would wrap negative in int32
     assert m._ids32(torch.tensor([[cfg.image_vocab_size]])).dtype == torch.int32
+
+
+def test_magvit2_lightning_checkpoint_loader(golden_dir):
+    """magvit2/models/lfqgan.py:85-119: a checkpoint with the reference's key layout (generator + `model_ema.*` buffers
+    named by the REFERENCE's LitEma + loss keys; tests/golden/make_golden_r2.py) loads into VQModel: stage=None takes
+    the live weights (what visualize.decode_latents_wrapper ends up using), stage='transformer' the EMA weights."""
+    path = os.path.join(golden_dir, "magvit_tiny.ckpt")
+    info = json.load(open(os.path.join(golden_dir, "magvit_tiny_keys.json")))
+    raw = torch.load(path, map_location="cpu", weights_only=False)["state_dict"]
+    assert sorted(raw) == info["keys"]
+    cfg = pkg.VQConfig(base_channels=info["config"]["base_channels"], ch_mult=tuple(info["config"]["ch_mult"]),
+                       num_res_blocks=info["config"]["num_res_blocks"])
+    m = pkg.VQModel.from_ckpt(path, cfg)
+    own = m.state_dict()
+    assert sorted(own) == sorted(k for k in raw if k.startswith(("encoder.", "decoder.")))    # loss.* / model_ema.* dropped
+    for k, v in own.items():
+        assert torch.equal(v, raw[k])
+    m2 = pkg.VQModel.from_ckpt(path, cfg, stage="transformer")
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v, raw["model_ema." + info["ema_map"][k]]) and not torch.equal(v, raw[k])
+    broken = {k: v for k, v in raw.items() if k != "decoder.conv_out.bias"}
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        torch.save({"state_dict": broken}, os.path.join(td, "b.ckpt"))
+        with pytest.raises(KeyError):
+            pkg.VQModel.from_ckpt(os.path.join(td, "b.ckpt"), cfg)
