@@ -32,7 +32,7 @@ class gn_config(C.Structure):
 class gn_vq_config(C.Structure):
     _fields_ = [("in_channels", C.c_int32), ("z_channels", C.c_int32), ("out_channels", C.c_int32),
                 ("base_channels", C.c_int32), ("num_blocks", C.c_int32), ("ch_mult", C.c_int32 * 8),
-                ("num_res_blocks", C.c_int32)]
+                ("num_res_blocks", C.c_int32), ("precision", C.c_int32)]
 
 
 _vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64

@@ -284,10 +284,17 @@ struct TcpBars {
   uint32_t tmem_slot, pad;
 };
 
-template <typename H>
+// HD = 32 (the in-tree 35M config, genie/configs/magvit_n32_h8_d256.json): the TMA boxes stay 64 columns wide and cover
+// the head PAIR (h & ~1, h | 1) - one 128-byte swizzle atom per row, exactly the HD = 64 shared-memory layout.  Head h
+// uses the 32-byte K slices [2 (h & 1), 2 (h & 1) + 2) of the atom for Q K^T (two MMAs instead of four); P V runs over
+// the full 64-wide V box (N = 64: the other head's 32 columns are computed and ignored - 4 S d FLOPs of a kernel that is
+// bound by the exponentials, not by the tensor pipe), and the epilogue reads, merges and stores only the head's own 32
+// accumulator columns (64-byte rows, SWIZZLE_64B staging and store box).
+template <typename H, int HD>
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 spatial_attn_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmO,
                                   int d, int n_heads, int n_items, float scale_log2e) {
+  static_assert(HD == 64 || HD == 32, "head_dim 64 or 32");
   constexpr int SK = TCP_SK;
   constexpr int BK = SK / 2;          // keys per softmax block
   constexpr uint32_t IDESC_QK = umma_idesc(H16<H>::UMMA_FMT, TCA_QROWS, SK, 0, 0);
@@ -337,10 +344,11 @@ spatial_attn_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmKV, cons
         uint8_t* st = smem + s * TCP_STAGE_BYTES;
         mbar_wait(&bars->empty[s], ((i >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&bars->full[s], TCP_STAGE_BYTES);
-        // the fused QKV rows are read exactly once (by this kernel): evict_first
-        tma_load_2d_hint(st, &tmKV, &bars->full[s], h * TCA_HD, f * SK, pol);                              // Q, 256 rows
-        tma_load_2d_hint(st + SK * TCA_ROWB, &tmKV, &bars->full[s], d + h * TCA_HD, f * SK, pol);          // K
-        tma_load_2d_hint(st + 2 * SK * TCA_ROWB, &tmKV, &bars->full[s], 2 * d + h * TCA_HD, f * SK, pol);  // V
+        // the fused QKV rows are read exactly once (by this kernel; twice for HD = 32, from L2): evict_first
+        const int c0 = HD == 64 ? h * TCA_HD : (h >> 1) * TCA_HD;       // first column of the 64-wide box
+        tma_load_2d_hint(st, &tmKV, &bars->full[s], c0, f * SK, pol);                              // Q, 256 rows
+        tma_load_2d_hint(st + SK * TCA_ROWB, &tmKV, &bars->full[s], d + c0, f * SK, pol);          // K
+        tma_load_2d_hint(st + 2 * SK * TCA_ROWB, &tmKV, &bars->full[s], 2 * d + c0, f * SK, pol);  // V
       }
     }
   } else if (warp == 1) {
@@ -350,8 +358,11 @@ spatial_attn_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmKV, cons
         const uint8_t* st = smem + (i & 1) * TCP_STAGE_BYTES;
         const uint64_t qd = umma_desc_kmajor_sw128(smem_u32(st + j * TCA_QROWS * TCA_ROWB));
         const uint64_t kd = umma_desc_kmajor_sw128(smem_u32(st + SK * TCA_ROWB));
+        // HD = 32: this head's two 32-byte K slices inside the pair's 128-byte atom
+        const int k0 = HD == 64 ? 0 : 2 * ((((int)blockIdx.x + i * (int)gridDim.x) % n_heads) & 1);
 #pragma unroll
-        for (int k = 0; k < TCA_HD / 16; ++k) umma_bf16(tmem + j * SK, qd + 2 * k, kd + 2 * k, IDESC_QK, k != 0);
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16(tmem + j * SK, qd + 2 * (k0 + k), kd + 2 * (k0 + k), IDESC_QK, k != 0);
         umma_commit(&bars->sready[j]);
       };
       auto issue_pv = [&](int i, int j, int blk) {   // O_blk = P_blk V[128 blk .. 128 blk + 128)
@@ -457,11 +468,12 @@ spatial_attn_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmKV, cons
       tc_fence_after();
       uint8_t* stq = smem + (i & 1) * TCP_STAGE_BYTES + j * TCA_QROWS * TCA_ROWB;   // dead Q tile = output staging
       {
-        uint32_t ra[64], rb[64];
-        tmem_ld_32x32b_x32(my_addr + BK / 2, *reinterpret_cast<uint32_t(*)[32]>(&ra[0]));
-        tmem_ld_32x32b_x32(my_addr + BK / 2 + 32, *reinterpret_cast<uint32_t(*)[32]>(&ra[32]));
-        tmem_ld_32x32b_x32(my_addr + BK + BK / 2, *reinterpret_cast<uint32_t(*)[32]>(&rb[0]));
-        tmem_ld_32x32b_x32(my_addr + BK + BK / 2 + 32, *reinterpret_cast<uint32_t(*)[32]>(&rb[32]));
+        uint32_t ra[HD], rb[HD];
+        const int oc = HD == 64 ? 0 : 32 * (h & 1);      // this head's accumulator columns inside the 64-wide O
+        tmem_ld_32x32b_x32(my_addr + BK / 2 + oc, *reinterpret_cast<uint32_t(*)[32]>(&ra[0]));
+        if (HD == 64) tmem_ld_32x32b_x32(my_addr + BK / 2 + 32, *reinterpret_cast<uint32_t(*)[32]>(&ra[HD - 32]));
+        tmem_ld_32x32b_x32(my_addr + BK + BK / 2 + oc, *reinterpret_cast<uint32_t(*)[32]>(&rb[0]));
+        if (HD == 64) tmem_ld_32x32b_x32(my_addr + BK + BK / 2 + 32, *reinterpret_cast<uint32_t(*)[32]>(&rb[HD - 32]));
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -472,9 +484,9 @@ spatial_attn_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmKV, cons
         const float inv = 1.f / (wa * lblk[0] + wb * lblk[1]);
         wa *= inv;
         wb *= inv;
-        uint8_t* srow = stq + row * TCA_ROWB;
+        uint8_t* srow = stq + row * (HD * 2);          // 128-byte rows / SWIZZLE_128B, or 64-byte rows / SWIZZLE_64B
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < HD / 8; ++c) {
           float o[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e)
@@ -484,13 +496,14 @@ spatial_attn_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmKV, cons
           v.y = pack_h2<H>(o[2], o[3]);
           v.z = pack_h2<H>(o[4], o[5]);
           v.w = pack_h2<H>(o[6], o[7]);
-          *reinterpret_cast<uint4*>(srow + ((c ^ (row & 7)) << 4)) = v;
+          const int sc = HD == 64 ? (c ^ (row & 7)) : (c ^ ((row >> 1) & 3));
+          *reinterpret_cast<uint4*>(srow + (sc << 4)) = v;
         }
       }
       fence_proxy_async_smem();
       named_bar_sync(1 + j, 128);
       if (gtid == 0) {
-        tma_store_2d(&tmO, stq, h * TCA_HD, f * SK + j * TCA_QROWS);
+        tma_store_2d(&tmO, stq, h * HD, f * SK + j * TCA_QROWS);
         tma_store_commit();
         tma_store_wait_read<0>();
         mbar_arrive(&bars->empty[i & 1]);
@@ -506,7 +519,7 @@ spatial_attn_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmKV, cons
   }
 }
 
-template <typename H>
+template <typename H, int HD>
 int launch_tc_persistent(const AttnArgs& a, int n_frames, cudaStream_t st) {
   const int d = a.n_heads * a.head_dim;
   const int64_t rows = (int64_t)n_frames * TCP_SK;
@@ -514,14 +527,15 @@ int launch_tc_persistent(const AttnArgs& a, int n_frames, cudaStream_t st) {
   const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
   GN_PROPAGATE(make_tensor_map_2d(&tmKV, a.qkv, H16<H>::TMAP, 2, 3 * d, rows, 3 * d, TCA_HD, TCP_SK,
                                   sw));
-  GN_PROPAGATE(make_tensor_map_2d(&tmO, a.out, H16<H>::TMAP, 2, d, rows, d, TCA_HD, TCA_QROWS, sw));
+  GN_PROPAGATE(make_tensor_map_2d(&tmO, a.out, H16<H>::TMAP, 2, d, rows, d, HD, TCA_QROWS,
+                                  HD == 64 ? sw : CU_TENSOR_MAP_SWIZZLE_64B));
   const int smem = TCP_STAGES * TCP_STAGE_BYTES + (int)sizeof(TcpBars) + 1024;
   static DevSmemOptIn optin;
-  GN_CUDA_CHECK(ensure_smem_optin(optin, spatial_attn_tc_persistent_kernel<H>, smem));
+  GN_CUDA_CHECK(ensure_smem_optin(optin, spatial_attn_tc_persistent_kernel<H, HD>, smem));
   const int sms = device_sm_count();
   const int n_items = n_frames * a.n_heads;
   const int grid = n_items < sms ? n_items : sms;
-  GN_CUDA_CHECK(launch_kernel(PC_SPATIAL, spatial_attn_tc_persistent_kernel<H>, dim3(grid), dim3(TCP_THREADS),
+  GN_CUDA_CHECK(launch_kernel(PC_SPATIAL, spatial_attn_tc_persistent_kernel<H, HD>, dim3(grid), dim3(TCP_THREADS),
                               (size_t)smem, st, tmKV, tmO, d, a.n_heads, n_items, a.scale * 1.4426950408889634f));
   ++g_launch_count;
   return GN_OK;
@@ -532,18 +546,25 @@ int launch_tc_persistent(const AttnArgs& a, int n_frames, cudaStream_t st) {
 bool tc_spatial_supported(const AttnArgs& a, int S) {
   const char* e = getenv("GENIE_B200_SPATIAL_TC");   // re-read per launch (tests compare both kernels in one process)
   const bool on = !(e && (e[0] == '0' || e[0] == 'n' || e[0] == 'N'));
-  return on && a.act_bf16 && a.head_dim == TCA_HD && (S == 128 || S == 256) && a.qk_gamma == nullptr;
+  if (!on || !a.act_bf16 || a.qk_gamma != nullptr) return false;
+  if (a.head_dim == TCA_HD) return S == 128 || S == 256;
+  // head_dim 32: persistent kernel only (S = 256), heads handled through 64-wide head-pair boxes
+  return a.head_dim == 32 && S == 256 && a.n_heads % 2 == 0 && !(e && e[0] == '1');
 }
 
 int tc_spatial_attention(const AttnArgs& a, int n_frames, int S, cudaStream_t st) {
   // GENIE_B200_SPATIAL_TC: unset / 2 = persistent kernel for S = 256, 1 = one-CTA-per-tile kernel, 0 = mma.sync kernel
   const char* e = getenv("GENIE_B200_SPATIAL_TC");
   const bool persistent = !(e && e[0] == '1');
+  if (a.head_dim == 32)
+    return a.fp16 ? launch_tc_persistent<f16, 32>(a, n_frames, st) : launch_tc_persistent<bf16, 32>(a, n_frames, st);
   if (a.fp16) {
-    if (S == 256) return persistent ? launch_tc_persistent<f16>(a, n_frames, st) : launch_tc_t<256, f16>(a, n_frames, st);
+    if (S == 256)
+      return persistent ? launch_tc_persistent<f16, 64>(a, n_frames, st) : launch_tc_t<256, f16>(a, n_frames, st);
     return launch_tc_t<128, f16>(a, n_frames, st);
   }
-  if (S == 256) return persistent ? launch_tc_persistent<bf16>(a, n_frames, st) : launch_tc_t<256, bf16>(a, n_frames, st);
+  if (S == 256)
+    return persistent ? launch_tc_persistent<bf16, 64>(a, n_frames, st) : launch_tc_t<256, bf16>(a, n_frames, st);
   return launch_tc_t<128, bf16>(a, n_frames, st);
 }
 

@@ -107,6 +107,7 @@ struct TcArgs {
   const float* qkn_g;   // qk-LayerNorm over 64-column groups of output columns [0, qkn_cols) (wide bf16 store epilogue)
   const float* qkn_b;
   int qkn_cols;
+  int red_add;   // fp32 store epilogue: out += tile (TMA reduce-add) instead of out = tile
 };
 
 template <typename OutT>
@@ -617,6 +618,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int cc = col0 - part * args.kv_d;
                 tma_store_4d(part == 1 ? &tmK : &tmV, st0 + buf * SM::OUT_STAGE_BYTES, cc % args.kv_hd, kv_frame,
                              cc / args.kv_hd, kv_pos);
+              } else if (sizeof(OutT) == 4 && args.red_add) {
+                tma_reduce_add_2d(&tmOut, st0 + buf * SM::OUT_STAGE_BYTES, col0, row0);
               } else {
                 tma_store_2d(&tmOut, st0 + buf * SM::OUT_STAGE_BYTES, col0, row0);
               }
@@ -740,6 +743,7 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
   }
   t.a_hint = a.a_evict_first;
   t.qkn_g = a.qkn_gamma; t.qkn_b = a.qkn_beta; t.qkn_cols = a.qkn_gamma ? a.qkn_cols : 0;
+  t.red_add = a.red_add;
   if ((t.qkn_cols > 0) != QKN || (QKN && !(SM::WIDE && EPI == EPI_STORE))) {
     set_error("qk-LayerNorm epilogue needs the wide bf16 store epilogue (N %% 128 == 0)");
     return GN_ERR_UNSUPPORTED;
@@ -752,7 +756,7 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
   }
   t.ln_stats = a.ln_stats; t.ln_np = a.ln_np; t.ln_d = a.ln_d; t.ln_colsum = a.ln_colsum; t.stats_out = a.stats_out;
   g_gemm_flops_issued += 2.0 * a.M * (double)a.N * a.K;
-  const int cat = EPI == EPI_RESID ? PC_GEMM_RESID : (EPI == EPI_GELU ? PC_GEMM_GELU : PC_GEMM_STORE);
+  const int cat = (EPI == EPI_RESID || a.red_add) ? PC_GEMM_RESID : (EPI == EPI_GELU ? PC_GEMM_GELU : PC_GEMM_STORE);
   if (CTAS == 2)
     GN_CUDA_CHECK(launch_kernel_cluster(cat, kern, dim3(grid), dim3(32 * (2 + SM::NUM_EPI_WARPS)), SM::TOTAL, stream, 2,
                                         tmA, tmB, tmO, tmO2, tmR, tmK, tmV, t));
@@ -799,6 +803,17 @@ int dispatch_n(const LinearArgs& a, cudaStream_t s) {
   // reads per MMA cycle), so those use 256 with a 3-stage ring.
   // 256-wide tiles run as CTA pairs (256 x 256 per pair, cta_group::2) unless disabled or a convolution
   const bool pair = env_on("GENIE_B200_PAIR", g_use_pair) && !a.conv && a.M > BLOCK_M;
+  // experiment switch for the N = 512 GEMMs (proj / fc2): GENIE_B200_BN512 = 64 | 128 | 256 (single CTA) | 1128 | 1256
+  // (CTA pair with 128 / 256-wide tiles)
+  if (a.N == 512 && !a.conv) {
+    const char* e = getenv("GENIE_B200_BN512");
+    const int v = e ? atoi(e) : 0;
+    if (v == 64) return dispatch_epi<InT, 64>(a, s);
+    if (v == 128) return dispatch_epi<InT, 128>(a, s);
+    if (v == 256) return dispatch_epi<InT, 256>(a, s);
+    if (v == 1128 && a.M > BLOCK_M) return dispatch_epi<InT, 128, 2>(a, s);
+    if (v == 1256 && a.M > BLOCK_M) return dispatch_epi<InT, 256, 2>(a, s);
+  }
   if (a.N % 256 == 0 && pair && (a.epi != EPI_RESID || a.K >= 1024 || env_on("GENIE_B200_PAIR_PROJ", false)))
     return dispatch_epi<InT, 256, 2>(a, s);
   if (a.N % 256 == 0 && (a.epi != EPI_RESID || a.K >= 1024 || env_on("GENIE_B200_PROJ256", false)))
@@ -817,7 +832,7 @@ __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const InT* __restrict__ A, int64_t lda, const InT* __restrict__ W, int64_t ldw,
                  const float* __restrict__ bias, const float* __restrict__ resid, int64_t ldr, OutT* __restrict__ out,
                  int64_t ldo, typename Half16Of<InT>::type* __restrict__ out2, int64_t ldo2, int M, int N, int K,
-                 int epi) {
+                 int epi, ConvGeom cg) {
   __shared__ float sa[SK][ST + 1];
   __shared__ float sw[SK][ST + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -827,7 +842,21 @@ gemm_simt_kernel(const InT* __restrict__ A, int64_t lda, const InT* __restrict__
     for (int i = threadIdx.x; i < ST * SK; i += 256) {
       const int r = i / SK, c = i % SK;
       const int gm = m0 + r, gn = n0 + r, gk = k0 + c;
-      sa[c][r] = (gm < M && gk < K) ? to_f32<InT>(A[(int64_t)gm * lda + gk]) : 0.f;
+      float av = 0.f;
+      if (gm < M && gk < K) {
+        if (cg.Cin > 0) {
+          // implicit GEMM 3x3 convolution, padding 1: row = output pixel (n, y, x), column = (tap, channel)
+          const int P = cg.Ho * cg.Wo;
+          const int n = gm / P, rem = gm % P, y = rem / cg.Wo, x = rem % cg.Wo;
+          const int tap = gk / cg.Cin, ci = gk % cg.Cin;
+          const int iy = y * cg.stride + tap / 3 - 1, ix = x * cg.stride + tap % 3 - 1;
+          if (iy >= 0 && iy < cg.Hi && ix >= 0 && ix < cg.Wi)
+            av = to_f32<InT>(A[(((int64_t)n * cg.Hi + iy) * cg.Wi + ix) * cg.Cin + ci]);
+        } else {
+          av = to_f32<InT>(A[(int64_t)gm * lda + gk]);
+        }
+      }
+      sa[c][r] = av;
       sw[c][r] = (gn < N && gk < K) ? to_f32<InT>(W[(int64_t)gn * ldw + gk]) : 0.f;
     }
     __syncthreads();
@@ -867,7 +896,7 @@ int launch_simt(const LinearArgs& a, cudaStream_t s) {
   gemm_simt_kernel<InT, OutT><<<grid, 256, 0, s>>>(
       static_cast<const InT*>(a.A), a.lda, static_cast<const InT*>(a.W), a.ldw, a.bias, a.resid, a.ldr,
       static_cast<OutT*>(a.out), a.ldo, static_cast<typename Half16Of<InT>::type*>(a.out2), a.ldo2, a.M, a.N, a.K,
-      a.epi);
+      a.epi, a.conv ? *a.conv : ConvGeom{0, 0, 0, 0, 0, 0, 1});
   GN_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;
   return GN_OK;
@@ -886,6 +915,8 @@ int linear_forward(const LinearArgs& a, cudaStream_t stream) {
   GN_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "linear_forward: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
   GN_REQUIRE(a.A && a.W && a.out, "linear_forward: null operand");
   GN_REQUIRE(a.epi != EPI_RESID || a.resid, "linear_forward: EPI_RESID needs a residual pointer");
+  GN_REQUIRE(!a.red_add || (a.epi == EPI_STORE && !a.out_bf16 && !a.force_simt && !a.conv && !a.round_out_tf32),
+             "red_add: fp32 store epilogue on the tensor path only");
   const int esz = a.in_bf16 ? 2 : 4;
   GN_REQUIRE(!(a.ln_stats || a.stats_out) || (!a.force_simt && a.N % 64 == 0),
              "folded LayerNorm / row statistics need the tensor path (N %% 64 == 0)");
@@ -893,12 +924,15 @@ int linear_forward(const LinearArgs& a, cudaStream_t stream) {
   GN_REQUIRE(!a.stats_out || a.epi == EPI_RESID, "row statistics are produced by the residual epilogue");
   if (a.conv) {
     const ConvGeom& g = *a.conv;
-    const int bk = 128 / esz;
-    GN_REQUIRE(!a.force_simt, "conv: tensor path only");
-    GN_REQUIRE(g.Cin % bk == 0 && a.K == 9 * g.Cin, "conv: Cin %d must be a multiple of %d and K == 9*Cin", g.Cin, bk);
-    GN_REQUIRE(a.N % 64 == 0, "conv: Cout %d must be a multiple of 64", a.N);
+    GN_REQUIRE(a.K == 9 * g.Cin, "conv: K == 9*Cin expected");
     GN_REQUIRE(g.stride == 1 || g.stride == 2, "conv: stride must be 1 or 2");
     GN_REQUIRE(a.M == g.Nimg * g.Ho * g.Wo, "conv: M != Nimg*Ho*Wo");
+  }
+  if (a.conv && !a.force_simt) {   // the fp32 exact mode (force_simt) takes any geometry on the CUDA-core kernel
+    const ConvGeom& g = *a.conv;
+    const int bk = 128 / esz;
+    GN_REQUIRE(g.Cin % bk == 0, "conv: Cin %d must be a multiple of %d", g.Cin, bk);
+    GN_REQUIRE(a.N % 64 == 0, "conv: Cout %d must be a multiple of 64", a.N);
     GN_REQUIRE((g.Ho * g.Wo) % 128 == 0 && (g.Wo >= 128 ? g.Wo % 128 == 0 : 128 % g.Wo == 0),
                "conv: output %dx%d not tileable by 128-pixel tiles", g.Ho, g.Wo);
     GN_REQUIRE(g.Wo >= 128 || g.Ho % (128 / g.Wo) == 0, "conv: Ho not a multiple of the tile height");
@@ -931,6 +965,7 @@ int linear_forward(const LinearArgs& a, cudaStream_t stream) {
     return a.fp16 ? dispatch_n<f16>(a, stream) : dispatch_n<bf16>(a, stream);
   }
   GN_REQUIRE(!a.kv_k, "K/V-cache output: operands not eligible for the tensor path");
+  GN_REQUIRE(!a.red_add, "red_add: operands not eligible for the tensor path");
   GN_REQUIRE(!a.qkn_gamma, "qk-LayerNorm epilogue: operands not eligible for the tensor path");
   if (!a.force_simt) ++g_fallback_launches;   // CUDA-core GEMM on a handle that did not ask for the fp32 mode: shape / alignment cliff
   if (a.in_bf16) {

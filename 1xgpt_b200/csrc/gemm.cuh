@@ -52,6 +52,8 @@ struct LinearArgs {
   const float* qkn_beta;
   int qkn_cols;
   int a_evict_first;  // 1: A is not read again after this GEMM (L2 evict_first hint on its loads)
+  int red_add;        // 1 (EPI_STORE, fp32 out, tensor path): out += A.W^T + bias through TMA reduce-add (the residual
+                      // update x += f(x) without loading x into the SM; bit-identical to EPI_RESID in place)
   const ConvGeom* conv; // non-null: implicit-GEMM 3x3 convolution (A = NHWC input, K = 9*Cin, M = Nimg*Ho*Wo)
   // LayerNorm folded into the epilogue (A holds the RAW bf16 rows, W holds W*diag(gamma)):
   //   out[m,n] = rstd[m] * (acc[m,n] - mean[m] * colsum[n]) + bias[n]        (bias already contains beta . W^T)

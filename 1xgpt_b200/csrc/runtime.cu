@@ -68,6 +68,11 @@ int device_sm_count() {
     int n = 0;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     sms[dev] = n > 0 ? n : 148;
+    // experiment: GENIE_B200_SM_DIV=k caps every persistent grid at SMs / k, so that `lanes = k` concurrent clip streams
+    // run side by side on disjoint SM sets (one lane's kernel drain / fill overlaps the other lane's compute)
+    const char* e = getenv("GENIE_B200_SM_DIV");
+    const int div = e ? atoi(e) : 1;
+    if (div > 1) sms[dev] = (sms[dev] / div) & ~1;
   }
   return sms[dev];
 }

@@ -95,9 +95,14 @@ int launch_stem_conv(const float* img, const float* w, float* out, int B, int H,
 // summation-order noise would flip bits of near-zero latents):
 //   stage 1: block (chunk of pixels, image) -> partial[n][chunk][g] = {sum, sumsq} in a fixed order
 //   stage 2: stats[n][g] = sum over chunks in index order (double)
+// The block that finishes LAST for an image (atomic ticket) folds that image's partials into stats[n][g] in chunk-index
+// order: which block is last varies from run to run, the summation order does not.  This replaces a separate
+// finalize launch (350 launches of 26 us per 64-image encode+decode in round 1).
 __global__ void __launch_bounds__(256)
-gn_partial_kernel(const float* __restrict__ x, double* __restrict__ partial, int HW, int C, int pix_per_block) {
+gn_partial_kernel(const float* __restrict__ x, double* __restrict__ partial, double* __restrict__ stats,
+                  unsigned int* __restrict__ tickets, int HW, int C, int pix_per_block) {
   __shared__ float s_sum[256], s_sq[256];
+  __shared__ bool s_last;
   const int n = blockIdx.y;
   const int cg = C / 32;                 // channels per group (4, 8, 16)
   const int vpp = C / 4;                 // float4 per pixel; 256 % vpp == 0 -> each thread owns one channel quad
@@ -124,48 +129,60 @@ gn_partial_kernel(const float* __restrict__ x, double* __restrict__ partial, int
     o[0] = a;
     o[1] = b2;
   }
-}
-// One block per image, one warp per group: lane l adds the chunks c = l, l + 32, ... in index order, then the 32 lane
-// sums are folded by a fixed shuffle tree - deterministic like the serial loop it replaces (26 us per launch for 512
-// chunks: 12 % of the tokenizer's time).
-__global__ void __launch_bounds__(1024) gn_finalize_kernel(const double* __restrict__ partial,
-                                                           double* __restrict__ stats, int chunks) {
-  const int n = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&tickets[n], 1u);
+    s_last = (t == gridDim.x - 1);
+    if (s_last) tickets[n] = 0;          // ready for the next launch on this stream
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // 8 threads per group: thread j of a group adds the chunks c = j, j + 8, ... in index order (<= 8 independent loads
+  // each), then the 8 sums are folded by a fixed shuffle tree
+  const int g = threadIdx.x >> 3, j = threadIdx.x & 7, chunks = gridDim.x;
   double a = 0.0, b = 0.0;
-  for (int c = lane; c < chunks; c += 32) {
-    const double2 p = *reinterpret_cast<const double2*>(partial + (((int64_t)n * chunks + c) * 32 + g) * 2);
+#pragma unroll 8
+  for (int c = j; c < chunks; c += 8) {
+    const double2 p = __ldcg(reinterpret_cast<const double2*>(partial + (((int64_t)n * chunks + c) * 32 + g) * 2));
     a += p.x;
     b += p.y;
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a += __shfl_down_sync(0xffffffffu, a, o);
-    b += __shfl_down_sync(0xffffffffu, b, o);
+  for (int o = 4; o > 0; o >>= 1) {
+    a += __shfl_down_sync(0xffffffffu, a, o, 8);
+    b += __shfl_down_sync(0xffffffffu, b, o, 8);
   }
-  if (lane == 0) {
+  if (j == 0) {
     stats[((int64_t)n * 32 + g) * 2] = a;
     stats[((int64_t)n * 32 + g) * 2 + 1] = b;
   }
 }
-// stats buffer layout: [B*64 doubles final stats][partials]
+// stats buffer layout: [64 doubles = 128 uint tickets at a FIXED place, zeroed at allocation][B*64 doubles final
+// stats][partials]; kStatsOff = offset of the final stats that the apply / head kernels read
+constexpr int kStatsOff = 64;
 static int gn_stats(const float* x, double* stats, int B, int HW, int C, cudaStream_t st) {
   GN_REQUIRE(C % 128 == 0 && 1024 % C == 0, "GroupNorm: C %d unsupported (128, 256, 512, 1024)", C);
-  const int ppb = HW >= 4096 ? 128 : (HW >= 1024 ? 32 : 8);
+  // <= 64 chunks per image: the last block's fold (below) is a short, latency-bound tail
+  int ppb = 8;
+  while (ceil_div(HW, ppb) > 64) ppb *= 2;
   const int chunks = ceil_div(HW, ppb);
   GN_REQUIRE(chunks <= 512, "GroupNorm: too many partial chunks");
-  double* partial = stats + (int64_t)B * 64;
-  gn_partial_kernel<<<dim3(chunks, B), 256, 0, st>>>(x, partial, HW, C, ppb);
+  GN_REQUIRE(B <= 128, "GroupNorm: at most 128 images per pass");
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(stats);
+  double* partial = stats + kStatsOff + (int64_t)B * 64;
+  gn_partial_kernel<<<dim3(chunks, B), 256, 0, st>>>(x, partial, stats + kStatsOff, tickets, HW, C, ppb);
   GN_CUDA_CHECK(cudaGetLastError());
-  gn_finalize_kernel<<<B, 1024, 0, st>>>(partial, stats, chunks);
-  GN_CUDA_CHECK(cudaGetLastError());
-  g_launch_count += 2;
+  ++g_launch_count;
   return GN_OK;
 }
 
-// y = swish(GN(x)) -> bf16 NHWC (the A operand of the next convolution)     improved_model.py:8-10,41-46
+// y = swish(GN(x)) -> NHWC in the operand format of the next convolution (bf16 / fp16 / fp32)  improved_model.py:8-10,41-46
+template <typename OutT>
 __global__ void __launch_bounds__(256)
 gn_apply_swish_kernel(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
-                      const float* __restrict__ beta, bf16* __restrict__ out, int HW, int C, int64_t total_vec) {
+                      const float* __restrict__ beta, OutT* __restrict__ out, int HW, int C, int64_t total_vec) {
   const int vec_per_pix = C / 4, cg = C / 32;
   const double cnt = (double)HW * cg;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
@@ -184,19 +201,28 @@ gn_apply_swish_kernel(const float* __restrict__ x, const double* __restrict__ st
                   (f.w - mean) * rstd * gm.w + bt.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) y[k] = y[k] / (1.f + __expf(-y[k]));
-    uint2 p;
-    p.x = pack_bf16x2(y[0], y[1]);
-    p.y = pack_bf16x2(y[2], y[3]);
-    reinterpret_cast<uint2*>(out)[i] = p;
+    if constexpr (sizeof(OutT) == 4) {
+      reinterpret_cast<float4*>(out)[i] = make_float4(y[0], y[1], y[2], y[3]);
+    } else {
+      uint2 p;
+      p.x = pack_h2<OutT>(y[0], y[1]);
+      p.y = pack_h2<OutT>(y[2], y[3]);
+      reinterpret_cast<uint2*>(out)[i] = p;
+    }
   }
 }
 
-int launch_gn_swish(const float* x, double* stats, const float* gamma, const float* beta, bf16* out, int B, int HW, int C,
-                    cudaStream_t st) {
+int launch_gn_swish(const float* x, double* stats, const float* gamma, const float* beta, void* out, int o16, int B,
+                    int HW, int C, cudaStream_t st) {
   GN_PROPAGATE(gn_stats(x, stats, B, HW, C, st));
   const int64_t total_vec = (int64_t)B * HW * (C / 4);
   const int g2 = (int)std::min<int64_t>(ceil_div64(total_vec, 256), 148 * 16);
-  gn_apply_swish_kernel<<<g2, 256, 0, st>>>(x, stats, gamma, beta, out, HW, C, total_vec);
+  if (o16 == 2)
+    gn_apply_swish_kernel<f16><<<g2, 256, 0, st>>>(x, stats + kStatsOff, gamma, beta, static_cast<f16*>(out), HW, C, total_vec);
+  else if (o16 == 1)
+    gn_apply_swish_kernel<bf16><<<g2, 256, 0, st>>>(x, stats + kStatsOff, gamma, beta, static_cast<bf16*>(out), HW, C, total_vec);
+  else
+    gn_apply_swish_kernel<float><<<g2, 256, 0, st>>>(x, stats + kStatsOff, gamma, beta, static_cast<float*>(out), HW, C, total_vec);
   GN_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;
   return GN_OK;
@@ -270,7 +296,7 @@ int launch_vq_head(const float* x, double* stats, const float* gamma, const floa
   GN_REQUIRE(Z <= 31, "LFQ: at most 31 bits");
   GN_PROPAGATE(gn_stats(x, stats, B, HW, C, st));
   const int n_pix = B * HW;
-  vq_head_kernel<<<ceil_div(n_pix, 8), 256, 0, st>>>(x, stats, gamma, beta, w, bias, ids, z_out, HW, C, Z, n_pix);
+  vq_head_kernel<<<ceil_div(n_pix, 8), 256, 0, st>>>(x, stats + kStatsOff, gamma, beta, w, bias, ids, z_out, HW, C, Z, n_pix);
   GN_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;
   return GN_OK;
@@ -329,11 +355,14 @@ int launch_vq_tail(const int32_t* ids, const float* w, const float* bias, float*
 // fixed order.  (The first version - one warp per pixel, weights gathered from global memory with a 9-float stride,
 // three warp reductions per pixel - ran 1.02 ms per 8 images against ~25 us of HBM time for its input.)
 constexpr int OC_PIX = 64;
+template <typename InT>
 __global__ void __launch_bounds__(128)
-out_conv_kernel(const bf16* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
+out_conv_kernel(const InT* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
                 float* __restrict__ out_f32, uint8_t* __restrict__ out_u8, int H, int W, int C) {
   extern __shared__ __align__(16) uint8_t oc_smem[];
-  const int pitch = C * 2 + 16;                               // bytes per staged pixel
+  constexpr int ES = (int)sizeof(InT);                        // 2 (bf16 / fp16) or 4 (fp32 exact mode)
+  constexpr int EPV = 16 / ES;                                // elements per 16-byte vector
+  const int pitch = C * ES + 16;                              // bytes per staged pixel
   uint8_t* sin = oc_smem;                                     // [3][OC_PIX + 2][pitch]
   float* sw = reinterpret_cast<float*>(oc_smem + 3 * (OC_PIX + 2) * pitch);   // [9][C][4]
   float* sred = sw + 9 * C * 4;                               // [4 slices][OC_PIX][3]
@@ -350,13 +379,13 @@ out_conv_kernel(const bf16* __restrict__ a, const float* __restrict__ w, const f
     reinterpret_cast<float4*>(sw)[i] = v;
   }
   // input patch, 16-byte vectors, zero outside the image
-  const int vec_per_pix = C / 8;
+  const int vec_per_pix = C / EPV;
   for (int i = tid; i < 3 * (OC_PIX + 2) * vec_per_pix; i += blockDim.x) {
     const int v = i % vec_per_pix, p = (i / vec_per_pix) % (OC_PIX + 2), r = i / (vec_per_pix * (OC_PIX + 2));
     const int yy = y + r - 1, xx = x0 + p - 1;
     uint4 val = make_uint4(0, 0, 0, 0);
     if (yy >= 0 && yy < H && xx >= 0 && xx < W)
-      val = *reinterpret_cast<const uint4*>(a + (((int64_t)n * H + yy) * W + xx) * C + v * 8);
+      val = *reinterpret_cast<const uint4*>(a + (((int64_t)n * H + yy) * W + xx) * C + v * EPV);
     *reinterpret_cast<uint4*>(sin + (r * (OC_PIX + 2) + p) * pitch + v * 16) = val;
   }
   __syncthreads();
@@ -364,17 +393,24 @@ out_conv_kernel(const bf16* __restrict__ a, const float* __restrict__ w, const f
   float acc[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
   for (int t = 0; t < 9; ++t) {
     const int r = t / 3, dx = t % 3;
-    const uint8_t* p0 = sin + (r * (OC_PIX + 2) + lane + dx) * pitch + slice * cps * 2;
+    const uint8_t* p0 = sin + (r * (OC_PIX + 2) + lane + dx) * pitch + slice * cps * ES;
     const uint8_t* p1 = p0 + 32 * pitch;
     const float4* wt = reinterpret_cast<const float4*>(sw) + t * C + slice * cps;
-    for (int c8 = 0; c8 < cps; c8 += 8) {
-      const uint4 u0 = *reinterpret_cast<const uint4*>(p0 + c8 * 2);
-      const uint4 u1 = *reinterpret_cast<const uint4*>(p1 + c8 * 2);
-      const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&u0);
-      const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&u1);
+    for (int c8 = 0; c8 < cps; c8 += EPV) {
+      const uint4 u0 = *reinterpret_cast<const uint4*>(p0 + c8 * ES);
+      const uint4 u1 = *reinterpret_cast<const uint4*>(p1 + c8 * ES);
+      const uint32_t* h0 = reinterpret_cast<const uint32_t*>(&u0);
+      const uint32_t* h1 = reinterpret_cast<const uint32_t*>(&u1);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 v0 = __bfloat1622float2(h0[k]), v1 = __bfloat1622float2(h1[k]);
+      for (int k = 0; k < EPV / 2; ++k) {
+        float2 v0, v1;
+        if constexpr (ES == 2) {
+          v0 = unpack_h2<InT>(h0[k]);
+          v1 = unpack_h2<InT>(h1[k]);
+        } else {
+          v0 = make_float2(__uint_as_float(h0[2 * k]), __uint_as_float(h0[2 * k + 1]));
+          v1 = make_float2(__uint_as_float(h1[2 * k]), __uint_as_float(h1[2 * k + 1]));
+        }
         const float4 wa = wt[c8 + 2 * k], wb = wt[c8 + 2 * k + 1];
         acc[0][0] = fmaf(v0.x, wa.x, acc[0][0]); acc[0][1] = fmaf(v0.x, wa.y, acc[0][1]); acc[0][2] = fmaf(v0.x, wa.z, acc[0][2]);
         acc[0][0] = fmaf(v0.y, wb.x, acc[0][0]); acc[0][1] = fmaf(v0.y, wb.y, acc[0][1]); acc[0][2] = fmaf(v0.y, wb.z, acc[0][2]);
@@ -400,33 +436,44 @@ out_conv_kernel(const bf16* __restrict__ a, const float* __restrict__ w, const f
     if (out_u8) out_u8[o] = (uint8_t)fminf(fmaxf((v + 1.f) * 127.5f, 0.f), 255.f);
   }
 }
-int launch_out_conv(const bf16* a, const float* w, const float* bias, float* out_f32, uint8_t* out_u8, int B, int H, int W,
-                    int C, cudaStream_t st) {
-  GN_REQUIRE(C % 32 == 0 && C <= 512, "output conv: C %d unsupported (multiple of 32, <= 512)", C);
-  const size_t smem = (size_t)3 * (OC_PIX + 2) * (C * 2 + 16) + (size_t)9 * C * 16 + (size_t)4 * OC_PIX * 3 * 4;
+template <typename InT>
+static int launch_out_conv_t(const InT* a, const float* w, const float* bias, float* out_f32, uint8_t* out_u8, int B, int H,
+                             int W, int C, cudaStream_t st) {
+  const size_t smem = (size_t)3 * (OC_PIX + 2) * (C * sizeof(InT) + 16) + (size_t)9 * C * 16 + (size_t)4 * OC_PIX * 3 * 4;
+  GN_REQUIRE(smem <= 227 * 1024, "output conv: C %d does not fit shared memory in this precision", C);
   static DevSmemOptIn optin;
-  GN_CUDA_CHECK(ensure_smem_optin(optin, out_conv_kernel, (int)smem));
+  GN_CUDA_CHECK(ensure_smem_optin(optin, out_conv_kernel<InT>, (int)smem));
   dim3 grid(ceil_div(W, OC_PIX), H, B);
-  out_conv_kernel<<<grid, 128, smem, st>>>(a, w, bias, out_f32, out_u8, H, W, C);
+  out_conv_kernel<InT><<<grid, 128, smem, st>>>(a, w, bias, out_f32, out_u8, H, W, C);
   GN_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;
   return GN_OK;
 }
+int launch_out_conv(const void* a, int o16, const float* w, const float* bias, float* out_f32, uint8_t* out_u8, int B, int H,
+                    int W, int C, cudaStream_t st) {
+  GN_REQUIRE(C % 32 == 0 && C <= 512, "output conv: C %d unsupported (multiple of 32, <= 512)", C);
+  if (o16 == 2) return launch_out_conv_t<f16>(static_cast<const f16*>(a), w, bias, out_f32, out_u8, B, H, W, C, st);
+  if (o16 == 1) return launch_out_conv_t<bf16>(static_cast<const bf16*>(a), w, bias, out_f32, out_u8, B, H, W, C, st);
+  return launch_out_conv_t<float>(static_cast<const float*>(a), w, bias, out_f32, out_u8, B, H, W, C, st);
+}
 
 // conv weight repack: PyTorch [Cout, Cin, kh, kw] fp32 -> [Cout, kh*kw, Cin] bf16 (tap-major K for the implicit GEMM)
-__global__ void repack_conv_w_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int taps) {
+template <typename OutT>
+__global__ void repack_conv_w_kernel(const float* __restrict__ w, OutT* __restrict__ out, int Cout, int Cin, int taps) {
   const int64_t total = (int64_t)Cout * Cin * taps;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int ci = (int)(i % Cin);
     const int t = (int)((i / Cin) % taps);
     const int co = (int)(i / ((int64_t)Cin * taps));
-    out[i] = __float2bfloat16_rn(w[((int64_t)co * Cin + ci) * taps + t]);
+    out[i] = from_f32<OutT>(w[((int64_t)co * Cin + ci) * taps + t]);
   }
 }
-int launch_repack_conv_w(const float* w, bf16* out, int Cout, int Cin, int taps, cudaStream_t st) {
+int launch_repack_conv_w(const float* w, void* out, int o16, int Cout, int Cin, int taps, cudaStream_t st) {
   const int64_t total = (int64_t)Cout * Cin * taps;
   const int grid = (int)std::min<int64_t>(ceil_div64(total, 256), 4096);
-  repack_conv_w_kernel<<<grid, 256, 0, st>>>(w, out, Cout, Cin, taps);
+  if (o16 == 2) repack_conv_w_kernel<f16><<<grid, 256, 0, st>>>(w, static_cast<f16*>(out), Cout, Cin, taps);
+  else if (o16 == 1) repack_conv_w_kernel<bf16><<<grid, 256, 0, st>>>(w, static_cast<bf16*>(out), Cout, Cin, taps);
+  else repack_conv_w_kernel<float><<<grid, 256, 0, st>>>(w, static_cast<float*>(out), Cout, Cin, taps);
   GN_CUDA_CHECK(cudaGetLastError());
   return GN_OK;
 }

@@ -16,7 +16,7 @@ using namespace gn;
 
 namespace {
 struct ConvW {
-  bf16* w = nullptr;      // [Cout, taps*Cin] bf16 (tensor path)
+  void* w = nullptr;      // [Cout, taps*Cin] in the operand format (bf16 / fp16 tensor path, fp32 exact mode)
   float* w_raw = nullptr; // original fp32 OIHW (direct kernels)
   float* b = nullptr;
   int cout = 0, cin = 0, taps = 0;
@@ -53,8 +53,10 @@ struct gn_vq {
   // workspace for `cap_imgs` images at full resolution
   int cap_imgs = 0, cap_H = 0, cap_W = 0;
   float *x = nullptr, *y = nullptr, *r = nullptr;
-  bf16* a = nullptr;
+  void* a = nullptr;     // convolution operand (GroupNorm + swish output / cast trunk) in the operand format
   double* stats = nullptr;
+  int o16 = 2;           // operand format: 2 = fp16 (default), 1 = bf16, 0 = fp32 on the CUDA-core kernels (exact mode)
+  size_t esz() const { return o16 ? 2 : 4; }
 };
 
 namespace {
@@ -87,14 +89,17 @@ int ensure_ws(gn_vq* m, int imgs, int H, int W) {
   GN_PROPAGATE(valloc(m, (void**)&m->x, elems * 4));
   GN_PROPAGATE(valloc(m, (void**)&m->y, elems * 4));
   GN_PROPAGATE(valloc(m, (void**)&m->r, elems * 4));
-  GN_PROPAGATE(valloc(m, (void**)&m->a, elems * 2));
-  GN_PROPAGATE(valloc(m, (void**)&m->stats, (size_t)imgs * (64 + 512 * 64) * sizeof(double)));  // final + partials
+  GN_PROPAGATE(valloc(m, (void**)&m->a, elems * m->esz()));
+  // final stats + last-block tickets (zeroed once; every launch leaves them at zero) + partials
+  const size_t stat_bytes = (64 + (size_t)imgs * (64 + 64 * 64)) * sizeof(double);
+  GN_PROPAGATE(valloc(m, (void**)&m->stats, stat_bytes));
+  GN_CUDA_CHECK(cudaMemset(m->stats, 0, stat_bytes));
   m->cap_imgs = imgs; m->cap_H = H; m->cap_W = W;
   return GN_OK;
 }
 
 // out[pix, Cout] = conv(a_bf16 NHWC) (+bias) (+resid)
-int conv(gn_vq* m, const ConvW& w, const bf16* a, int B, int Hi, int Wi, int stride, const float* resid, float* out,
+int conv(gn_vq* m, const ConvW& w, const void* a, int B, int Hi, int Wi, int stride, const float* resid, float* out,
          cudaStream_t st) {
   const int Ho = Hi / stride, Wo = Wi / stride;
   LinearArgs la{};
@@ -102,7 +107,8 @@ int conv(gn_vq* m, const ConvW& w, const bf16* a, int B, int Hi, int Wi, int str
   la.A = a; la.lda = w.cin; la.W = w.w; la.ldw = (int64_t)w.taps * w.cin; la.bias = w.b;
   la.resid = resid; la.ldr = w.cout; la.out = out; la.ldo = w.cout; la.out2 = nullptr; la.ldo2 = w.cout;
   la.M = B * Ho * Wo; la.N = w.cout; la.K = w.taps * w.cin;
-  la.epi = resid ? EPI_RESID : EPI_STORE; la.in_bf16 = 1; la.out_bf16 = 0; la.force_simt = 0;
+  la.epi = resid ? EPI_RESID : EPI_STORE; la.in_bf16 = m->o16 != 0; la.fp16 = m->o16 == 2; la.out_bf16 = 0;
+  la.force_simt = m->o16 == 0;
   la.conv = w.taps == 9 ? &g : nullptr;
   return linear_forward(la, st);
 }
@@ -110,16 +116,16 @@ int conv(gn_vq* m, const ConvW& w, const bf16* a, int B, int Hi, int Wi, int str
 // ResBlock (improved_model.py:36-51): x -> x + / nin(x) + conv2(swish(GN(conv1(swish(GN(x))))));  result in m->x
 int resblock(gn_vq* m, const ResW& rw, int B, int H, int W, cudaStream_t st) {
   const int HW = H * W;
-  GN_PROPAGATE(launch_gn_swish(m->x, m->stats, rw.n1.g, rw.n1.b, m->a, B, HW, rw.cin, st));
+  GN_PROPAGATE(launch_gn_swish(m->x, m->stats, rw.n1.g, rw.n1.b, m->a, m->o16, B, HW, rw.cin, st));
   GN_PROPAGATE(conv(m, rw.c1, m->a, B, H, W, 1, nullptr, m->y, st));
   const float* resid = m->x;
   if (rw.cin != rw.cout) {
     // 1x1 shortcut on the raw input (improved_model.py:34,49)
-    GN_PROPAGATE(launch_prep(m->x, m->a, 1, nullptr, nullptr, B * HW, rw.cin, 1.f, 1, 1, -1, st));
+    GN_PROPAGATE(launch_prep(m->x, m->a, m->o16, nullptr, nullptr, B * HW, rw.cin, 1.f, 1, 1, -1, st));
     GN_PROPAGATE(conv(m, rw.nin, m->a, B, H, W, 1, nullptr, m->r, st));
     resid = m->r;
   }
-  GN_PROPAGATE(launch_gn_swish(m->y, m->stats, rw.n2.g, rw.n2.b, m->a, B, HW, rw.cout, st));
+  GN_PROPAGATE(launch_gn_swish(m->y, m->stats, rw.n2.g, rw.n2.b, m->a, m->o16, B, HW, rw.cout, st));
   GN_PROPAGATE(conv(m, rw.c2, m->a, B, H, W, 1, resid, rw.cin != rw.cout ? m->x : m->x, st));
   return GN_OK;
 }
@@ -137,8 +143,8 @@ int set_conv(gn_vq* m, ConvW& c, const std::string& leaf, const float* src, cons
     c.cout = (int)shape[0]; c.cin = (int)shape[1]; c.taps = (int)(shape[2] * shape[3]);
     GN_PROPAGATE(put_f32(m, &c.w_raw, src, numel, st));
     if (tensor_path) {
-      if (!c.w) GN_PROPAGATE(valloc(m, (void**)&c.w, (size_t)numel * 2));
-      GN_PROPAGATE(launch_repack_conv_w(src, c.w, c.cout, c.cin, c.taps, st));
+      if (!c.w) GN_PROPAGATE(valloc(m, (void**)&c.w, (size_t)numel * m->esz()));
+      GN_PROPAGATE(launch_repack_conv_w(src, c.w, m->o16, c.cout, c.cin, c.taps, st));
     }
     return GN_OK;
   }
@@ -190,6 +196,9 @@ int gn_vq_create(gn_vq** out, const gn_vq_config* cfg, int device) {
   GN_REQUIRE(m, "out of host memory");
   m->cfg = *cfg;
   m->device = device;
+  GN_REQUIRE(cfg->precision == GN_PREC_BF16 || cfg->precision == GN_PREC_FP16 || cfg->precision == GN_PREC_FP32,
+             "MAGVIT2 path: precision must be GN_PREC_FP16, GN_PREC_BF16 or GN_PREC_FP32 (got %d)", cfg->precision);
+  m->o16 = cfg->precision == GN_PREC_FP16 ? 2 : (cfg->precision == GN_PREC_BF16 ? 1 : 0);
   m->nb = cfg->num_blocks;
   for (int i = 0; i < m->nb; ++i) m->ch.push_back(cfg->base_channels * cfg->ch_mult[i]);
   m->enc_down.assign(m->nb, std::vector<ResW>(cfg->num_res_blocks));
@@ -296,7 +305,7 @@ int gn_vq_encode(gn_vq* m, const float* img, int B, int H, int W, int32_t* ids, 
       for (int j = 0; j < m->cfg.num_res_blocks; ++j) GN_PROPAGATE(resblock(m, m->enc_down[i][j], n, h, w, st));
       if (i < nb - 1) {
         // downsample: 3x3 stride 2 padding 1 with bias, on the raw trunk (no norm) (improved_model.py:90,113)
-        GN_PROPAGATE(launch_prep(m->x, m->a, 1, nullptr, nullptr, n * h * w, m->ch[i], 1.f, 1, 1, -1, st));
+        GN_PROPAGATE(launch_prep(m->x, m->a, m->o16, nullptr, nullptr, n * h * w, m->ch[i], 1.f, 1, 1, -1, st));
         GN_PROPAGATE(conv(m, m->enc_ds[i], m->a, n, h, w, 2, nullptr, m->y, st));
         std::swap(m->x, m->y);
         h /= 2; w /= 2;
@@ -332,14 +341,14 @@ int gn_vq_decode(gn_vq* m, const int32_t* ids, int B, int h0, int w0, int little
       for (int j = 0; j < m->cfg.num_res_blocks; ++j) GN_PROPAGATE(resblock(m, m->dec_up[i][j], n, h, w, st));
       if (i > 0) {
         // Upsampler: conv3x3 C -> 4C (+bias) then depth-to-space (improved_model.py:222-237)
-        GN_PROPAGATE(launch_prep(m->x, m->a, 1, nullptr, nullptr, n * h * w, m->ch[i], 1.f, 1, 1, -1, st));
+        GN_PROPAGATE(launch_prep(m->x, m->a, m->o16, nullptr, nullptr, n * h * w, m->ch[i], 1.f, 1, 1, -1, st));
         GN_PROPAGATE(conv(m, m->dec_us[i], m->a, n, h, w, 1, nullptr, m->y, st));
         GN_PROPAGATE(launch_depth_to_space(m->y, m->x, n, h, w, m->ch[i], st));
         h *= 2; w *= 2;
       }
     }
-    GN_PROPAGATE(launch_gn_swish(m->x, m->stats, m->dec_norm.g, m->dec_norm.b, m->a, n, h * w, m->ch[0], st));
-    GN_PROPAGATE(launch_out_conv(m->a, m->dec_out.w_raw, m->dec_out.b, img_f32 ? img_f32 + (int64_t)b0 * 3 * H * W : nullptr,
+    GN_PROPAGATE(launch_gn_swish(m->x, m->stats, m->dec_norm.g, m->dec_norm.b, m->a, m->o16, n, h * w, m->ch[0], st));
+    GN_PROPAGATE(launch_out_conv(m->a, m->o16, m->dec_out.w_raw, m->dec_out.b, img_f32 ? img_f32 + (int64_t)b0 * 3 * H * W : nullptr,
                                  img_u8 ? img_u8 + (int64_t)b0 * 3 * H * W : nullptr, n, h, w, m->ch[0], st));
   }
   return GN_OK;

@@ -116,8 +116,11 @@ class _VqHandle:
 class VQModel(nn.Module):
     """Inference part of magvit2/models/lfqgan.py VQModel: encode -> tokens, tokens -> decode."""
 
-    def __init__(self, config: Optional[VQConfig] = None):
+    def __init__(self, config: Optional[VQConfig] = None, precision: str = "fp16"):
         super().__init__()
+        if precision not in ("fp16", "bf16", "fp32"):
+            raise ValueError(f"precision must be 'fp16' (default), 'bf16' or 'fp32' (exact mode), got {precision!r}")
+        self.precision = precision
         self.config = config or VQConfig()
         self.encoder = Encoder(self.config)
         self.decoder = Decoder(self.config)
@@ -148,14 +151,14 @@ class VQModel(nn.Module):
                                "there is no CPU fallback")
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
         d = self.__dict__
-        if d["_native"] is None or d["_native_dev"] != idx:
+        if d["_native"] is None or d["_native_dev"] != (idx, self.precision):
             c = self.config
             mult = (C.c_int32 * 8)(*(list(c.ch_mult) + [0] * (8 - len(c.ch_mult))))
             cfg = _lib.gn_vq_config(in_channels=c.in_channels, z_channels=c.z_channels, out_channels=c.out_channels,
                                     base_channels=c.base_channels, num_blocks=len(c.ch_mult), ch_mult=mult,
-                                    num_res_blocks=c.num_res_blocks)
+                                    num_res_blocks=c.num_res_blocks, precision=_lib.PRECISIONS[self.precision])
             d["_native"] = _VqHandle(cfg, idx)
-            d["_native_dev"] = idx
+            d["_native_dev"] = (idx, self.precision)
             d["_dirty"] = True
         if d["_dirty"]:
             h = d["_native"]
@@ -198,8 +201,9 @@ class VQModel(nn.Module):
         return self
 
     @classmethod
-    def from_ckpt(cls, path, config: Optional[VQConfig] = None, stage: Optional[str] = None) -> "VQModel":
-        return cls(config).init_from_ckpt(path, stage=stage)
+    def from_ckpt(cls, path, config: Optional[VQConfig] = None, stage: Optional[str] = None,
+                  precision: str = "fp16") -> "VQModel":
+        return cls(config, precision=precision).init_from_ckpt(path, stage=stage)
 
     # ------------------------------------------------------------------ API
     @torch.no_grad()

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define GN_ABI_VERSION 3
+#define GN_ABI_VERSION 4
 
 /* precision modes of the linear layers / activations */
 #define GN_PREC_BF16 0 /* tcgen05 kind::f16, bf16 operands+activations, fp32 accumulate/residual/LN/softmax */
@@ -178,6 +178,9 @@ typedef struct gn_vq_config { /* mirrors magvit2/config.py:12-18 (VQConfig) */
   int32_t num_blocks;     /* len(ch_mult) = 5 */
   int32_t ch_mult[8];     /* (1, 1, 2, 2, 4) */
   int32_t num_res_blocks; /* 2 */
+  int32_t precision;      /* operand format of the convolutions: GN_PREC_FP16 (default of the Python mirror), GN_PREC_BF16
+                             (visualize.py:97 decodes in bf16), or GN_PREC_FP32: every convolution on the CUDA-core
+                             fp32 kernel - the exact mode in which the LFQ token ids equal the reference's */
 } gn_vq_config;
 int gn_vq_create(gn_vq** out, const gn_vq_config* cfg, int device);
 void gn_vq_destroy(gn_vq* m);

@@ -23,7 +23,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 cfg, sd = bench.synth_state_dict()
-m = pkg.STMaskGIT(pkg.GenieConfig(**bench.MODEL_KW), precision="bf16", kv_cache=True, chunk_tokens=32768)
+m = pkg.STMaskGIT(pkg.GenieConfig(**bench.MODEL_KW), precision=os.environ.get("GENIE_PRECISION", "fp16"), kv_cache=True, chunk_tokens=32768)
 m.load_state_dict(sd)
 m = m.to(f"cuda:{local}")
 clips = torch.randint(0, cfg.image_vocab_size, (B * world, cfg.T * cfg.S), generator=torch.Generator().manual_seed(5))

@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 pkg = importlib.import_module("1xgpt_b200")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-m = pkg.VQModel()
+m = pkg.VQModel(precision=os.environ.get("GENIE_PRECISION", "fp16"))
 # seeded synthetic weights (no checkpoint reachable): fan-in scaled convs, GroupNorm affine near identity
 _g = torch.Generator().manual_seed(31)
 _sd = {}

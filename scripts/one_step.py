@@ -22,7 +22,7 @@ lib = pkg._lib.load()
 dev = torch.device("cuda", 0)
 torch.cuda.set_stream(torch.cuda.Stream(dev))
 cfg, sd = bench.synth_state_dict()
-m = pkg.STMaskGIT(cfg, precision="bf16", kv_cache=True, cuda_graphs=False)
+m = pkg.STMaskGIT(cfg, precision=os.environ.get("GENIE_PRECISION", "fp16"), kv_cache=True, cuda_graphs=False)
 m.load_state_dict(sd)
 m = m.to(dev)
 h = m._handle()

@@ -297,3 +297,61 @@ def test_spatial_attention_tcgen05(lib, monkeypatch, n_frames, S, H, peaked, var
     assert torch.isfinite(outs[0].float()).all()
     assert e_tc < 6e-3          # bf16 P and bf16 output rounding
     assert e_tc < 1.5 * e_mma + 1e-3
+
+
+@pytest.mark.parametrize("fp16", [False, True])
+@pytest.mark.parametrize("n_frames,H,hd,peaked", [(3, 8, 32, False), (40, 8, 32, True), (2, 2, 32, True), (3, 8, 64, True)])
+def test_spatial_attention_tcgen05_head_dim_32_and_fp16(lib, n_frames, H, hd, peaked, fp16):
+    """round 2: (a) head_dim 32 (the in-tree 35M config) on the persistent tcgen05 kernel - 64-wide head-PAIR boxes,
+    the head's own two 32-byte K slices for Q K^T, its own 32 accumulator columns in the epilogue: a wrong slice / column
+    mapping mixes the two heads of a pair and cannot pass; 40 x 8 items > 148 CTAs exercises the ring; (b) IEEE fp16
+    data (kernel | 0x100) through the same kernels: P and the output are rounded to 11 bits instead of 8."""
+    L, _l = lib
+    S, d = 256, H * hd
+    dt = torch.float16 if fp16 else torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(300 + n_frames + H + hd)
+    qkv = torch.randn(n_frames * S, 3 * d, device="cuda", generator=g)
+    if peaked:
+        qkv[:, :2 * d] *= 3.0
+    qkv = qkv.to(dt).contiguous()
+    scale = 1.0 / math.sqrt(hd)
+    flag = 0x100 if fp16 else 0
+    outs = []
+    for kernel in (0, 1):                                   # 0: tcgen05, 1: mma.sync kernel it replaces
+        out = torch.full((n_frames * S, d), float("nan"), device="cuda", dtype=dt)
+        _l.check(L.gn_spatial_attention(P(qkv), P(out), n_frames, S, H, hd, scale, kernel | flag, None))
+        torch.cuda.synchronize()
+        outs.append(out)
+    ref = _spatial_ref(qkv, n_frames, S, H, hd, scale)
+    e_tc, e_mma = rel_fro(outs[0].double(), ref), rel_fro(outs[1].double(), ref)
+    print(f"spatial attention hd={hd} fp16={fp16} F={n_frames} H={H} peaked={peaked}: tcgen05 rel {e_tc:.3e}, "
+          f"mma.sync rel {e_mma:.3e}")
+    assert torch.isfinite(outs[0].float()).all()
+    assert e_tc < (8e-4 if fp16 else 6e-3)
+    assert e_tc < 1.5 * e_mma + (2e-4 if fp16 else 1e-3)
+
+
+@pytest.mark.parametrize("epi,N,K", [(0, 1536, 512), (1, 2048, 512), (2, 512, 2048), (2, 512, 512)])
+def test_linear_fp16_operands(lib, epi, N, K):
+    """the tcgen05 linear kernel with IEEE fp16 operands / outputs (in_bf16 = out_bf16 = 2) against float64."""
+    L, _l = lib
+    M = 1000                                                 # ragged last tile
+    g = torch.Generator(device="cuda").manual_seed(7 + epi + N)
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
+    b = torch.randn(N, device="cuda", generator=g)
+    r = torch.randn(M, N, device="cuda", generator=g) if epi == 2 else None
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32 if epi == 2 else torch.float16)
+    out2 = torch.empty(M, N, device="cuda", dtype=torch.float16) if epi == 2 else None
+    _l.check(L.gn_linear_forward(P(a), P(w), P(b), P(r), P(out), P(out2), M, N, K, epi, 2, 0 if epi == 2 else 2, 0, None))
+    torch.cuda.synchronize()
+    ref = a.double() @ w.double().t() + b.double()
+    if epi == 1:
+        ref = torch.nn.functional.gelu(ref)
+    if epi == 2:
+        ref = ref + r.double()
+    err = rel_fro(out.double(), ref)
+    print(f"fp16 linear epi={epi} N={N} K={K}: rel {err:.3e}")
+    assert err < (1e-5 if epi == 2 else 4e-4)                # fp32 residual output vs fp16-rounded output
+    if out2 is not None:
+        assert rel_fro(out2.double(), ref) < 4e-4

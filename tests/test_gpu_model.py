@@ -23,7 +23,8 @@ pytestmark = pytest.mark.gpu
 
 TINY = ["tiny_preln", "tiny_qknorm_mup", "tiny_qknorm"]
 BAR = 1e-3                         # north star: logits within 1e-3 rel of the reference forward
-TOL = {"fp32": 2e-5, "tf32": BAR, "fp16": BAR, "bf16": 2e-2}
+# tiny fixtures, measured on B200: fp32 2.2e-7, tf32 / fp16 2.6e-4..3.6e-4, bf16 2.1e-3..2.8e-3
+TOL = {"fp32": 2e-5, "tf32": 5.5e-4, "fp16": 5.5e-4, "bf16": 4.2e-3}
 # measured on B200 (profiles/r02_parity.jsonl, scripts/parity_report.py): (fixture, mode) -> (logits rel, final-token
 # agreement of MaskGIT-2 at frame 8)
 MEASURED = {
@@ -231,7 +232,7 @@ def test_folded_layernorm_option(name):
     print(f"{name}: fold vs separate LN rel {rel_fro(a, b):.3e}")
     assert rel_fro(a, b) < 1e-2
     if ref is not None:
-        assert rel_fro(a, ref) < TOL["bf16"]
+        assert rel_fro(a, ref) < 2e-2          # fold_ln is an off-by-default option with a known accuracy cost
 
 
 def test_decoder_forward_seam():
@@ -305,8 +306,8 @@ def test_production_forward_loss_35m_config0(precision):
     err = rel_fro(sub, torch.from_numpy(z["logits_sub"]))
     print(f"35M forward {precision}: loss {float(out.loss):.6f} (ref {float(z['fwd_loss']):.6f}, |d| {dl:.2e}), "
           f"acc |d| {da:.2e}, logits rel {err:.3e}")
-    # measured |d loss|: fp32 <1e-6, fp16 / tf32 ~1e-5, bf16 ~1e-4 (CE averages 12k positions)
-    assert dl < {"fp32": 2e-5, "fp16": 1e-4, "tf32": 1e-4, "bf16": 1e-3}[precision]
+    # measured |d loss| on B200: fp32 9.5e-7, fp16 6.7e-6, tf32 5.7e-6, bf16 2.45e-4 (x 1.5; CE averages 12k positions)
+    assert dl < {"fp32": 2e-6, "fp16": 1e-5, "tf32": 1e-5, "bf16": 3.7e-4}[precision]
     assert da < (1e-9 if precision == "fp32" else 1e-3)
     assert err < (TOL["fp32"] if precision == "fp32" else BAR if precision != "bf16" else 1.2e-2)
 
@@ -545,3 +546,21 @@ def test_two_devices_in_one_process():
         s, _ = m.maskgit_generate(p.to(dev), 8, maskgit_steps=2, noise=torch.from_numpy(z["noise"]))
         outs.append(s.cpu())
     assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3])
+
+
+@pytest.mark.parametrize("name", ["genie35m", "genie138m"])
+def test_reduce_add_residual_epilogue_is_bit_identical(name, monkeypatch):
+    """GENIE_B200_RED_EPI=1: residual GEMMs that emit no 16-bit copy update x with a TMA reduce-add of (acc + bias)
+    instead of loading x into the SM.  Same fp32 sum (x + (acc + bias)), so logits and tokens are bit-identical."""
+    z, kw, cfg, sd = _prod_setup(name)
+    ids = torch.from_numpy(z["ids"]).long()
+    outs = {}
+    for red in ("0", "1"):
+        monkeypatch.setenv("GENIE_B200_RED_EPI", red)
+        m = build_b200_model(kw, sd, precision="fp16", kv_cache=True)
+        lg = m.compute_logits(ids.cuda()).cpu()
+        p = ids.clone()
+        p[:, 8:] = cfg.mask_token_id
+        s, _ = m.maskgit_generate(p.cuda(), 8, maskgit_steps=2, noise=torch.from_numpy(z["noise"]))
+        outs[red] = (lg, s.cpu())
+    assert torch.equal(outs["0"][0], outs["1"][0]) and torch.equal(outs["0"][1], outs["1"][1])
