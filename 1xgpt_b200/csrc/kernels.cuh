@@ -57,6 +57,13 @@ int launch_temporal_attention_v2(const AttnArgs& a, int nb, int S, int T, int t0
 // generic standalone attention over [n_seq, n_tok] (SelfAttention.forward contract, any small shape)
 int launch_generic_attention(const AttnArgs& a, int n_seq, int n_tok, int causal, cudaStream_t st);
 
+// ---- readout_sample.cu: readout GEMM fused with the factored softmax / argmax / confidence (temperature 0).
+// A [R, K] 16-bit rows of the decoded frame, W [NV*512, K], bias [NV*512] fp32 -> samples [R], conf [R]; logits
+// [R, NV*512] fp32 only when `logits` != nullptr.
+bool readout_sample_supported(int V, int K, int is_16bit);
+int launch_readout_sample(const void* A, const void* W, const float* bias, float* logits, int32_t* samples, float* conf,
+                          int R, int K, int NV, int fp16, cudaStream_t st);
+
 // ---- decode.cu
 // factored softmax / argmax-or-categorical / confidence of one frame's logits rows [R, NV*V]  (st_mask_git.py:171-190)
 // uniform: nullptr = greedy argmax; else [R, NV] uniforms in [0,1) for the inverse-CDF categorical draw

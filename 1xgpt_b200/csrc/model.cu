@@ -67,6 +67,7 @@ struct gn_model {
   float* stats = nullptr; // [n, d/64, 2] row-statistics partials for the folded LayerNorm
   int qkn_epi = 0;        // qk-LayerNorm applied by the QKV GEMM epilogue (bf16, head_dim 64): the attention kernels then
                           // see already-normalised q / k and the tcgen05 spatial + temporal v2 kernels apply
+  int fuse_readout = 1;   // temperature-0 decode: readout GEMM fused with softmax / argmax / confidence (readout_sample.cu)
   int red_epi = 0;        // residual GEMMs that need no 16-bit copy of the new stream update x through TMA reduce-add
   int tv2 = 0;            // temporal attention v2: head-major K/V caches written by the temporal QKV GEMM epilogue
   void* scr_k = nullptr;  // [chunk clips * S][H][T][hd] scratch K/V for tv2 when the persistent cache is off
@@ -583,6 +584,22 @@ int readout(gn_model* m, int nb, int Tact, int tsel, float* out_rows, cudaStream
                 0, st);
 }
 
+// readout of local frame `tsel` fused with the factored softmax / argmax / confidence (readout_sample.cu): ids and
+// confidences of clips [b0, b0 + nb) go straight to samples / conf; the logits rows are written only when `logits_rows`
+// is non-null (step-0 logits of maskgit_generate, CE of evaluate).  reference: st_mask_git.py:262 + :171-190.
+int readout_and_sample(gn_model* m, int nb, int Tact, int tsel, float* logits_rows, int32_t* samples, float* conf,
+                       cudaStream_t st) {
+  const gn_config& c = m->cfg;
+  const int R = nb * c.S;
+  const float mult = c.use_mup ? 256.0f / c.d_model : 1.0f;
+  GN_PROPAGATE(launch_prep(m->x, m->a, m->o16(), nullptr, nullptr, R, c.d_model, mult, c.S, Tact, tsel, st, 0));
+  m->flops_executed += 2.0 * R * (double)m->C * c.d_model;
+  m->bytes_executed += (double)R * c.d_model * (4.0 + 2.0 * m->esz()) + (double)m->C * c.d_model * m->esz() +
+                       (logits_rows ? (double)R * m->C * 4.0 : 0.0) + 8.0 * R;
+  return launch_readout_sample(m->a, m->out_w, m->out_b, logits_rows, samples, conf, R, c.d_model, c.num_factored_vocabs,
+                               m->fp16, st);
+}
+
 __global__ void fill_i32_kernel(int32_t* p, int64_t clip_stride, int64_t off, int64_t per_clip, int B, int32_t v) {
   const int64_t total = (int64_t)B * per_clip;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -634,6 +651,11 @@ int maskgit_impl(gn_model* m, int32_t* prompt, int B, int out_t, int steps, int 
       GN_CUDA_CHECK(cudaEventRecord(m->lane_fork, st));
       for (int i = 1; i < used; ++i) GN_CUDA_CHECK(cudaStreamWaitEvent(m->lane_stream[i], m->lane_fork, 0));
     }
+    // temperature 0 on the 16-bit tensor path: readout GEMM fused with the decode math; the logits rows are only
+    // materialised when this step's logits are consumed (step-0 return value / CE)
+    const bool need_logits = step == 0 && (logits0 != nullptr || ce_targets != nullptr);
+    const bool fused = m->fuse_readout && uniform == nullptr && m->out_b != nullptr &&
+                       readout_sample_supported(c.factored_vocab_size, c.d_model, m->act_bf16 && !m->force_simt);
     int rc = GN_OK;
     for (int b0 = 0, ci = 0; b0 < B && rc == GN_OK; b0 += cc, ++ci) {
       const int nb = std::min(cc, B - b0);
@@ -641,7 +663,12 @@ int maskgit_impl(gn_model* m, int32_t* prompt, int B, int out_t, int steps, int 
       cudaStream_t ls = li == 0 ? st : m->lane_stream[li];
       select_lane(m, li);
       rc = forward_chunk(m, prompt, b0, nb, t0, Tact, cache, ls);
-      if (rc == GN_OK) rc = readout(m, nb, Tact, out_t - t0, m->logits_frame + (int64_t)b0 * S * m->C, ls);
+      if (rc != GN_OK) break;
+      if (fused)
+        rc = readout_and_sample(m, nb, Tact, out_t - t0, need_logits ? m->logits_frame + (int64_t)b0 * S * m->C : nullptr,
+                                m->samples_tmp + (int64_t)b0 * S, m->conf + (int64_t)b0 * S, ls);
+      else
+        rc = readout(m, nb, Tact, out_t - t0, m->logits_frame + (int64_t)b0 * S * m->C, ls);
     }
     select_lane(m, 0);
     if (used > 1) {   // join (also on the error path: the caller's stream must not run ahead of the side lanes)
@@ -660,8 +687,9 @@ int maskgit_impl(gn_model* m, int32_t* prompt, int B, int out_t, int steps, int 
     }
     // uniform [steps, B, S, NV]: Categorical draw of this step (st_mask_git.py:182-187); nullptr = argmax
     const float* un = uniform ? uniform + (int64_t)step * B * S * c.num_factored_vocabs : nullptr;
-    GN_PROPAGATE(launch_sample(m->logits_frame, B * S, c.factored_vocab_size, c.num_factored_vocabs, un,
-                               m->samples_tmp, m->conf, st));
+    if (!fused)
+      GN_PROPAGATE(launch_sample(m->logits_frame, B * S, c.factored_vocab_size, c.num_factored_vocabs, un,
+                                 m->samples_tmp, m->conf, st));
     const bool last = step == steps - 1;
     const int n_mask = last ? 0 : (int)std::ceil(std::cos((step + 1.0) / steps * M_PI / 2.0) * S);
     const float* cf = nullptr;
@@ -770,6 +798,8 @@ int gn_model_create(gn_model** out, const gn_config* cfg, int device) {
     // 1893 -> 1925 frames/s, results bit-identical (tests/test_gpu_model.py)
     const char* e = getenv("GENIE_B200_RED_EPI");
     m->red_epi = e ? (e[0] != '0') : 1;
+    const char* f = getenv("GENIE_B200_FUSED_READOUT");   // 0: readout GEMM + sample_kernel (two launches, logits via HBM)
+    m->fuse_readout = f ? (f[0] != '0') : 1;
   }
   m->lanes = cfg->lanes <= 0 ? 1 : std::min<int>(cfg->lanes, gn_model::kMaxLanes);   // measured neutral on B200: off by default
   m->hid = (int)(cfg->d_model * cfg->mlp_ratio);

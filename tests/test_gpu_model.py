@@ -564,3 +564,36 @@ def test_reduce_add_residual_epilogue_is_bit_identical(name, monkeypatch):
         s, _ = m.maskgit_generate(p.cuda(), 8, maskgit_steps=2, noise=torch.from_numpy(z["noise"]))
         outs[red] = (lg, s.cpu())
     assert torch.equal(outs["0"][0], outs["1"][0]) and torch.equal(outs["0"][1], outs["1"][1])
+
+
+@pytest.mark.parametrize("name", ["genie35m", "genie138m", "genie138m_qknorm_mup"])
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_fused_readout_sample_matches_two_kernel_path(name, precision, monkeypatch):
+    """readout_sample.cu (readout GEMM + factored softmax / argmax / confidence in one kernel; logits only written when
+    the caller consumes them) against the readout GEMM + sample_kernel pair it replaces: same tokens and step-0 logits
+    for MaskGIT-2 with injected noise, and for confidence-driven ('greedy') unmasking, which orders by the fused
+    kernel's confidences."""
+    z, kw, cfg, sd = _prod_setup(name)
+    ids = torch.from_numpy(z["ids"]).long()
+    B = ids.shape[0]
+    prompt0 = ids.clone()
+    prompt0[:, 8:] = cfg.mask_token_id
+    noise = torch.from_numpy(z["noise"])
+    res = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("GENIE_B200_FUSED_READOUT", fused)
+        m = build_b200_model(kw, sd, precision=precision, kv_cache=True)
+        p = prompt0.clone().cuda()
+        s, fl = m.maskgit_generate(p, 8, maskgit_steps=2, temperature=0.0, noise=noise)
+        pg = prompt0.clone().cuda()
+        sg, _ = m.maskgit_generate(pg, 8, maskgit_steps=3, temperature=0.0, unmask_mode="greedy")
+        gen = m.generate(ids[:, :14].reshape(B, -1).cuda(), None, max_new_tokens=2 * cfg.S, maskgit_steps=2,
+                         noise=torch.stack([noise, noise]))          # logits never requested: the no-logits variant
+        res[fused] = (s.cpu(), fl.cpu(), sg.cpu(), gen.cpu())
+    d = float((res["1"][1] - res["0"][1]).abs().max())
+    print(f"{name} {precision}: fused vs two-kernel logits max|d| {d:.3e}, tokens equal {torch.equal(res['1'][0], res['0'][0])}, "
+          f"greedy agreement {float((res['1'][2] == res['0'][2]).float().mean()):.4f}")
+    assert d < 1e-5
+    assert torch.equal(res["1"][0], res["0"][0])
+    assert torch.equal(res["1"][3], res["0"][3])
+    assert float((res["1"][2] == res["0"][2]).float().mean()) >= 0.99
