@@ -464,17 +464,21 @@ int launch_temporal_t(const AttnArgs& a, int B, int S, int T, int t0, int Tq, vo
 // n_stages-deep mbarrier ring ahead of the consumers.  Key r of a position always sits at tile row r, whatever
 // (t0, Tq) a call uses, so the cached decode stays bit-identical to the dense 16-frame forward.
 // =====================================================================================
-__device__ __forceinline__ uint32_t line_off(int line, int c) {      // SWIZZLE_128B, region base aligned to 1024 B
-  return (uint32_t)(line * 128 + ((c ^ (line & 7)) << 4));
+// byte offset of 16-byte chunk c of `line` (one (frame, head) row of HD elements) in a TMA-swizzled region whose base
+// is aligned to 1024 B: SWIZZLE_128B for 128-byte lines (HD = 64), SWIZZLE_64B for 64-byte lines (HD = 32)
+template <int HD>
+__device__ __forceinline__ uint32_t line_off(int line, int c) {
+  if (HD == 64) return (uint32_t)(line * 128 + ((c ^ (line & 7)) << 4));
+  return (uint32_t)(line * 64 + ((c ^ ((line >> 1) & 3)) << 4));
 }
 
-template <typename E>
+template <typename E, int HD>
 __global__ void __launch_bounds__(576, 1)
 temporal_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, int n_pos,
                         int S, int H, int t0, int Tq, int n_stages, int rq_bytes, int rk_bytes, float scale_log2e,
                         int hint) {
-  constexpr int HD = 64;
+  static_assert(HD == 64 || HD == 32, "head_dim 64 or 32");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = rq_bytes + 2 * rk_bytes;
@@ -547,9 +551,9 @@ temporal_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     uint32_t qo[HD / 16], ko[HD / 16], vo[HD / 16];
 #pragma unroll
     for (int kk = 0; kk < HD / 16; ++kk) {
-      qo[kk] = line_off(qrow * H + h, 2 * kk + (mi >> 1));
-      ko[kk] = line_off(h * Tk + krow, 2 * kk + (mi & 1));
-      vo[kk] = line_off(h * Tk + vrow, 2 * kk + (mi >> 1));
+      qo[kk] = line_off<HD>(qrow * H + h, 2 * kk + (mi >> 1));
+      ko[kk] = line_off<HD>(h * Tk + krow, 2 * kk + (mi & 1));
+      vo[kk] = line_off<HD>(h * Tk + vrow, 2 * kk + (mi >> 1));
     }
     int st = 0;
     uint32_t ph = 0;
@@ -620,12 +624,12 @@ temporal_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       if (g < Tq) {
 #pragma unroll
         for (int c = 0; c < HD / 8; ++c)
-          *reinterpret_cast<uint32_t*>(base + line_off(g * H + h, c) + t4 * 4) = pack_h2<E>(o[c][0] * i0, o[c][1] * i0);
+          *reinterpret_cast<uint32_t*>(base + line_off<HD>(g * H + h, c) + t4 * 4) = pack_h2<E>(o[c][0] * i0, o[c][1] * i0);
       }
       if (g + 8 < Tq) {
 #pragma unroll
         for (int c = 0; c < HD / 8; ++c)
-          *reinterpret_cast<uint32_t*>(base + line_off((g + 8) * H + h, c) + t4 * 4) =
+          *reinterpret_cast<uint32_t*>(base + line_off<HD>((g + 8) * H + h, c) + t4 * 4) =
               pack_h2<E>(o[c][2] * i1, o[c][3] * i1);
       }
       fence_proxy_async_smem();
@@ -636,10 +640,11 @@ temporal_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   }
 }
 
-template <typename E>
+template <typename E, int HD>
 int launch_temporal_v2(const AttnArgs& a, int nb, int S, int T, int t0, int Tq, const void* kc, const void* vc,
                        cudaStream_t st) {
-  const int H = a.n_heads, HD = 64, d = H * HD, Tk = t0 + Tq;
+  const int H = a.n_heads, d = H * HD, Tk = t0 + Tq;
+  const CUtensorMapSwizzle tsw = HD == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   const int n_pos = nb * S;
   CUtensorMap tmQ, tmK, tmV, tmO;
   {
@@ -648,14 +653,14 @@ int launch_temporal_v2(const AttnArgs& a, int nb, int S, int T, int t0, int Tq, 
     const int64_t so[3] = {HD * 2, (int64_t)d * 2, (int64_t)S * d * 2};
     const int box[4] = {HD, H, 1, Tq};
     GN_PROPAGATE(make_tensor_map_nd(&tmQ, a.qkv, H16<E>::TMAP, 4, dims, sq, box,
-                                    CU_TENSOR_MAP_SWIZZLE_128B));
+                                    tsw));
     GN_PROPAGATE(make_tensor_map_nd(&tmO, a.out, H16<E>::TMAP, 4, dims, so, box,
-                                    CU_TENSOR_MAP_SWIZZLE_128B));
+                                    tsw));
     const int64_t dk[3] = {HD, T, (int64_t)H * n_pos};
     const int64_t sk[2] = {HD * 2, (int64_t)T * HD * 2};
     const int bk[3] = {HD, Tk, H};
-    GN_PROPAGATE(make_tensor_map_nd(&tmK, kc, H16<E>::TMAP, 3, dk, sk, bk, CU_TENSOR_MAP_SWIZZLE_128B));
-    GN_PROPAGATE(make_tensor_map_nd(&tmV, vc, H16<E>::TMAP, 3, dk, sk, bk, CU_TENSOR_MAP_SWIZZLE_128B));
+    GN_PROPAGATE(make_tensor_map_nd(&tmK, kc, H16<E>::TMAP, 3, dk, sk, bk, tsw));
+    GN_PROPAGATE(make_tensor_map_nd(&tmV, vc, H16<E>::TMAP, 3, dk, sk, bk, tsw));
   }
   const int rq = (Tq * H * HD * 2 + 1023) & ~1023, rk = (Tk * H * HD * 2 + 1023) & ~1023;
   const int stage = rq + 2 * rk;
@@ -667,7 +672,7 @@ int launch_temporal_v2(const AttnArgs& a, int nb, int S, int T, int t0, int Tq, 
   if (ns > 8) ns = 8;
   GN_REQUIRE(ns >= 2, "temporal attention v2: a stage of %d bytes does not fit twice in shared memory", stage);
   const int smem = ns * stage + 1024 + 2 * ns * 8;
-  auto kern = temporal_attn_v2_kernel<E>;
+  auto kern = temporal_attn_v2_kernel<E, HD>;
   static DevSmemOptIn optin;
   GN_CUDA_CHECK(ensure_smem_optin(optin, kern, 227 * 1024));
   const int sms = device_sm_count();
@@ -705,15 +710,19 @@ int generic_temporal_attention(const AttnArgs& a, int B, int S, int T, int t0, i
                                cudaStream_t st);
 
 bool temporal_v2_supported(const AttnArgs& a, int S, int T) {
-  return a.act_bf16 && a.head_dim == 64 && a.n_heads <= 16 && T <= 16 && S % 32 == 0 && a.qk_gamma == nullptr;
+  return a.act_bf16 && (a.head_dim == 64 || a.head_dim == 32) && a.n_heads <= 16 && T <= 16 && S % 32 == 0 &&
+         a.qk_gamma == nullptr;
 }
 int launch_temporal_attention_v2(const AttnArgs& a, int nb, int S, int T, int t0, int Tq, const void* kcache,
                                  const void* vcache, cudaStream_t st) {
   GN_REQUIRE(temporal_v2_supported(a, S, T), "temporal attention v2: unsupported shape");
   GN_REQUIRE(t0 >= 0 && Tq >= 1 && t0 + Tq <= T, "temporal attention: bad frame range t0=%d Tq=%d T=%d", t0, Tq, T);
   GN_REQUIRE(kcache && vcache, "temporal attention v2 reads K/V from the head-major caches");
-  return a.fp16 ? launch_temporal_v2<f16>(a, nb, S, T, t0, Tq, kcache, vcache, st)
-                : launch_temporal_v2<bf16>(a, nb, S, T, t0, Tq, kcache, vcache, st);
+  if (a.head_dim == 32)
+    return a.fp16 ? launch_temporal_v2<f16, 32>(a, nb, S, T, t0, Tq, kcache, vcache, st)
+                  : launch_temporal_v2<bf16, 32>(a, nb, S, T, t0, Tq, kcache, vcache, st);
+  return a.fp16 ? launch_temporal_v2<f16, 64>(a, nb, S, T, t0, Tq, kcache, vcache, st)
+                : launch_temporal_v2<bf16, 64>(a, nb, S, T, t0, Tq, kcache, vcache, st);
 }
 
 int launch_spatial_attention(const AttnArgs& a, int n_frames, int S, int force_generic, cudaStream_t st) {

@@ -52,7 +52,7 @@ constexpr int res_bufs(int block_n, bool dual, int /*ctas*/) { return (block_n >
 // its own 128 rows of A and ONE HALF of the B tile, so a k-block costs A + B/2 bytes of L2->SM traffic per SM instead
 // of A + B: the linear layers of this model (K = 512 / 2048) are bound by the chip-wide L2->SM throughput
 // (~6.2 KB per L2 clock, profiles/), not by the tensor pipe.
-template <int BLOCK_N, int EPI, typename OutT, bool DUAL, int CTAS = 1>
+template <int BLOCK_N, int EPI, typename OutT, bool DUAL, int CTAS = 1, bool NARROW = false>
 struct GemmSmem {
   static constexpr int NUM_EPI_WARPS = EpiCfg<EPI>::WARPS;
   static constexpr int COLS_PER_WARP = BLOCK_N / (NUM_EPI_WARPS / 4);   // columns of the tile one warp handles
@@ -62,7 +62,8 @@ struct GemmSmem {
   // 128B-swizzle atom) and leave as ONE TMA store of 32 rows x 64 columns: full 128-byte lines instead of 64-byte
   // halves (for the temporal K/V caches: one (position, head, frame) row of head_dim 64 per line) and half as many
   // bulk stores per tile
-  static constexpr bool WIDE = EPI != EPI_RESID && sizeof(OutT) == 2 && COLS_PER_WARP % (2 * EPI_COLS) == 0;
+  // NARROW: 32-column staging even for 16-bit outputs (K/V-cache rows of head_dim 32 are 64-byte lines)
+  static constexpr bool WIDE = EPI != EPI_RESID && sizeof(OutT) == 2 && COLS_PER_WARP % (2 * EPI_COLS) == 0 && !NARROW;
   static constexpr int EPI_BUF_BYTES = 32 * EPI_COLS * (int)sizeof(OutT) * (WIDE ? 2 : 1);
   static constexpr int CHUNKS_PER_BUF = WIDE ? 2 : 1;
   static constexpr int STORE_BUFS_RAW = (COLS_PER_WARP / (EPI_COLS * CHUNKS_PER_BUF)) * EPI_BUF_BYTES <= 8192
@@ -164,13 +165,13 @@ __device__ __forceinline__ void stage_row_chunk_wide(uint8_t* buf, uint32_t lane
 template <typename InT> struct Half16Of { typedef InT type; };
 template <> struct Half16Of<float> { typedef bf16 type; };
 
-template <typename InT, int BLOCK_N, int EPI, typename OutT, bool DUAL, int CTAS, bool QKN>
+template <typename InT, int BLOCK_N, int EPI, typename OutT, bool DUAL, int CTAS, bool QKN, bool NARROW>
 __global__ void __launch_bounds__(32 * (2 + EpiCfg<EPI>::WARPS), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
                     const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const TcArgs args) {
-  using SM = GemmSmem<BLOCK_N, EPI, OutT, DUAL, CTAS>;
+  using SM = GemmSmem<BLOCK_N, EPI, OutT, DUAL, CTAS, NARROW>;
   constexpr int NUM_EPI_WARPS = SM::NUM_EPI_WARPS;
   constexpr int STAGES = SM::STAGES;
   constexpr int BLOCK_K = TILE_K_BYTES / (int)sizeof(InT);     // 64 (bf16) or 32 (tf32)
@@ -649,9 +650,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-template <typename InT, int BLOCK_N, int EPI, typename OutT, bool DUAL, int CTAS = 1, bool QKN = false>
+template <typename InT, int BLOCK_N, int EPI, typename OutT, bool DUAL, int CTAS = 1, bool QKN = false,
+          bool NARROW = false>
 int launch_tc(const LinearArgs& a, cudaStream_t stream) {
-  using SM = GemmSmem<BLOCK_N, EPI, OutT, DUAL, CTAS>;
+  using SM = GemmSmem<BLOCK_N, EPI, OutT, DUAL, CTAS, NARROW>;
   constexpr int BLOCK_K = TILE_K_BYTES / (int)sizeof(InT);
   const CUtensorMapDataType in_dt = H16<InT>::TMAP;
   const CUtensorMapDataType out_dt = H16<OutT>::TMAP;
@@ -704,7 +706,7 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
     tmK = tmO;
     tmV = tmO;
   }
-  auto kern = gemm_tcgen05_kernel<InT, BLOCK_N, EPI, OutT, DUAL, CTAS, QKN>;
+  auto kern = gemm_tcgen05_kernel<InT, BLOCK_N, EPI, OutT, DUAL, CTAS, QKN, NARROW>;
   static DevSmemOptIn optin;
   GN_CUDA_CHECK(ensure_smem_optin(optin, kern, SM::TOTAL));
   const int num_tiles = ceil_div(a.M, BLOCK_M * CTAS) * (a.N / BLOCK_N);
@@ -773,6 +775,10 @@ int dispatch_epi(const LinearArgs& a, cudaStream_t s) {
   if (a.epi == EPI_STORE) {
     if constexpr (sizeof(InT) == 2 && BLOCK_N >= 128) {
       if (a.out_bf16 && a.qkn_gamma) return launch_tc<InT, BLOCK_N, EPI_STORE, O16, false, CTAS, true>(a, s);
+    }
+    if constexpr (sizeof(InT) == 2) {   // K/V-cache rows of head_dim 32: 32-column (64-byte) stores
+      if (a.out_bf16 && a.kv_k && a.kv_hd == EPI_COLS)
+        return launch_tc<InT, BLOCK_N, EPI_STORE, O16, false, CTAS, false, true>(a, s);
     }
     return a.out_bf16 ? launch_tc<InT, BLOCK_N, EPI_STORE, O16, false, CTAS>(a, s)
                       : launch_tc<InT, BLOCK_N, EPI_STORE, float, false, CTAS>(a, s);

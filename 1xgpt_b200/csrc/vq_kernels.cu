@@ -155,8 +155,12 @@ gn_partial_kernel(const float* __restrict__ x, double* __restrict__ partial, dou
     b += __shfl_down_sync(0xffffffffu, b, o, 8);
   }
   if (j == 0) {
-    stats[((int64_t)n * 32 + g) * 2] = a;
-    stats[((int64_t)n * 32 + g) * 2 + 1] = b;
+    // mean and 1 / sqrt(var + eps) of the group in double, handed to the apply / head kernels as ONE float2 (they used
+    // to redo this double-precision division and square root per element: FP64 runs at 1/64 rate on this part)
+    const double cnt = (double)HW * (C / 32);
+    const double mean = a / cnt;
+    const double var = fmax(b / cnt - mean * mean, 0.0);
+    reinterpret_cast<float2*>(stats)[(int64_t)n * 32 + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-6)));
   }
 }
 // stats buffer layout: [64 doubles = 128 uint tickets at a FIXED place, zeroed at allocation][B*64 doubles final
@@ -184,16 +188,14 @@ __global__ void __launch_bounds__(256)
 gn_apply_swish_kernel(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
                       const float* __restrict__ beta, OutT* __restrict__ out, int HW, int C, int64_t total_vec) {
   const int vec_per_pix = C / 4, cg = C / 32;
-  const double cnt = (double)HW * cg;
+  const float2* mr = reinterpret_cast<const float2*>(stats);       // {mean, rstd} per (image, group)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
     const int v = (int)(i % vec_per_pix);
     const int64_t pix = i / vec_per_pix;
     const int n = (int)(pix / HW);
     const int g = (v * 4) / cg;
-    const double s = stats[((int64_t)n * 32 + g) * 2], q = stats[((int64_t)n * 32 + g) * 2 + 1];
-    const double mean_d = s / cnt;
-    const double var_d = fmax(q / cnt - mean_d * mean_d, 0.0);
-    const float mean = (float)mean_d, rstd = (float)(1.0 / sqrt(var_d + 1e-6));
+    const float2 ms = __ldg(mr + (int64_t)n * 32 + g);
+    const float mean = ms.x, rstd = ms.y;
     const float4 f = reinterpret_cast<const float4*>(x)[i];
     const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + v);
     const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + v);
@@ -270,15 +272,14 @@ vq_head_kernel(const float* __restrict__ x, const double* __restrict__ stats, co
   const int lane = threadIdx.x & 31;
   const int n = pix / HW;
   const int cg = C / 32;
-  const double cnt = (double)HW * cg;
+  const float2* mr = reinterpret_cast<const float2*>(stats);       // {mean, rstd} per (image, group)
   float acc[32];
 #pragma unroll
   for (int z = 0; z < 32; ++z) acc[z] = 0.f;
   for (int c = lane; c < C; c += 32) {
     const int g = c / cg;
-    const double s = stats[((int64_t)n * 32 + g) * 2], q = stats[((int64_t)n * 32 + g) * 2 + 1];
-    const double mean_d = s / cnt;
-    const float mean = (float)mean_d, rstd = (float)(1.0 / sqrt(fmax(q / cnt - mean_d * mean_d, 0.0) + 1e-6));
+    const float2 ms = __ldg(mr + (int64_t)n * 32 + g);
+    const float mean = ms.x, rstd = ms.y;
     float y = (x[(int64_t)pix * C + c] - mean) * rstd * gamma[c] + beta[c];
     y = y / (1.f + __expf(-y));
     for (int z = 0; z < Z; ++z) acc[z] = fmaf(y, w[(int64_t)z * C + c], acc[z]);

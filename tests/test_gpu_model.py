@@ -352,18 +352,19 @@ GEN8_FIRST_FRAME_FLOOR = {"fp16": 0.99, "tf32": 0.99, "bf16": 0.98}
 
 
 def test_no_fallback_launches_on_production_shapes():
-    """GENIE_138M (both flag sets): every launch of a cached generate step is the intended Blackwell kernel - no
+    """GENIE_138M (both flag sets) and the in-tree 35M config (head_dim 32): every launch of a cached generate step is the intended Blackwell kernel - no
     CUDA-core GEMM, no mma.sync / generic attention (gn_fallback_launches stays constant)."""
     lib = importlib.import_module("1xgpt_b200")._lib.load()
-    for name in ("genie138m", "genie138m_qknorm_mup"):
+    for name in ("genie138m", "genie138m_qknorm_mup", "genie35m"):
         z, kw, cfg, sd = _prod_setup(name)
         ids = torch.from_numpy(z["ids"]).long()
         for precision in ("fp16", "bf16"):
             m = build_b200_model(kw, sd, precision=precision, kv_cache=True)
             m.compute_logits(ids.cuda())                       # uploads weights, dense forward
             f0 = lib.gn_fallback_launches()
-            m.generate(ids[:, :8].reshape(1, -1).cuda(), None, max_new_tokens=8 * cfg.S, maskgit_steps=2,
-                       noise=torch.rand(8, 1, 1, cfg.S))
+            nb = ids.shape[0]
+            m.generate(ids[:, :8].reshape(nb, -1).cuda(), None, max_new_tokens=8 * cfg.S, maskgit_steps=2,
+                       noise=torch.rand(8, 1, nb, cfg.S))
             m.compute_logits(ids.cuda())
             assert lib.gn_fallback_launches() == f0, (name, precision)
 
@@ -442,11 +443,13 @@ def test_lanes_are_bit_identical(graphs):
         assert torch.equal(outs[1][1], outs[lanes][1])
 
 
-def test_temporal_v2_matches_legacy_kernel(monkeypatch):
-    """Temporal attention v2 (TMA-fed, K/V written into head-major caches by the QKV GEMM epilogue) against the
+@pytest.mark.parametrize("name", ["genie138m", "genie35m"])
+def test_temporal_v2_matches_legacy_kernel(monkeypatch, name):
+    """(genie35m: head_dim 32 - 64-byte K/V cache lines, SWIZZLE_64B boxes, narrow GEMM epilogue staging.)
+    Temporal attention v2 (TMA-fed, K/V written into head-major caches by the QKV GEMM epilogue) against the
     legacy per-warp cp.async kernel (GENIE_B200_TEMPORAL_V2=0): same mma operands in the same tile positions, so the
     logits must agree to fp32 summation noise, and cached generation must equal dense generation bit for bit."""
-    z, kw, cfg, sd = _prod_setup("genie138m")
+    z, kw, cfg, sd = _prod_setup(name)
     ids = torch.from_numpy(z["ids"]).long()
     B = ids.shape[0]
     logits = {}
