@@ -607,6 +607,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               buf = (buf + 1 == SM::OUT_BUFS) ? 0 : buf + 1;
             }
           } else {
+            if constexpr (QKN && NARROW) {
+              // qk-LayerNorm for head_dim 32: this 32-column chunk is one head of this thread's row
+              if (col0 < args.qkn_cols) {
+                float s1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < EPI_COLS; ++j) s1 += v[j];
+                const float mean = s1 * (1.f / EPI_COLS);
+                float s2 = 0.f;
+#pragma unroll
+                for (int j = 0; j < EPI_COLS; ++j) { const float dl = v[j] - mean; s2 = fmaf(dl, dl, s2); }
+                const float rstd = rsqrtf(s2 * (1.f / EPI_COLS) + 1e-5f);
+                const float4* g4 = reinterpret_cast<const float4*>(args.qkn_g);
+                const float4* b4 = reinterpret_cast<const float4*>(args.qkn_b);
+#pragma unroll
+                for (int j = 0; j < EPI_COLS / 4; ++j) {
+                  const float4 ga = __ldg(g4 + j), ba = __ldg(b4 + j);
+                  v[4 * j] = (v[4 * j] - mean) * rstd * ga.x + ba.x;
+                  v[4 * j + 1] = (v[4 * j + 1] - mean) * rstd * ga.y + ba.y;
+                  v[4 * j + 2] = (v[4 * j + 2] - mean) * rstd * ga.z + ba.z;
+                  v[4 * j + 3] = (v[4 * j + 3] - mean) * rstd * ga.w + ba.w;
+                }
+              }
+            }
             // the staging buffer about to be written was last stored from OUT_BUFS steps ago
             if (lane == 0) tma_store_wait_read<SM::OUT_BUFS - 1>();
             __syncwarp();
@@ -746,8 +769,9 @@ int launch_tc(const LinearArgs& a, cudaStream_t stream) {
   t.a_hint = a.a_evict_first;
   t.qkn_g = a.qkn_gamma; t.qkn_b = a.qkn_beta; t.qkn_cols = a.qkn_gamma ? a.qkn_cols : 0;
   t.red_add = a.red_add;
-  if ((t.qkn_cols > 0) != QKN || (QKN && !(SM::WIDE && EPI == EPI_STORE))) {
-    set_error("qk-LayerNorm epilogue needs the wide bf16 store epilogue (N %% 128 == 0)");
+  if ((t.qkn_cols > 0) != QKN || (QKN && !((SM::WIDE || NARROW) && EPI == EPI_STORE && sizeof(OutT) == 2))) {
+    set_error("qk-LayerNorm epilogue needs the 16-bit store epilogue (head_dim 64: wide staging, N %% 128 == 0; "
+              "head_dim 32: narrow staging)");
     return GN_ERR_UNSUPPORTED;
   }
   t.w_prefetch = env_on("GENIE_B200_W_PREFETCH", false) ? 1 : 0;   // measured: 257.9 vs 257.3 ms per step -> off
@@ -773,12 +797,14 @@ template <typename InT, int BLOCK_N, int CTAS = 1>
 int dispatch_epi(const LinearArgs& a, cudaStream_t s) {
   typedef typename Half16Of<InT>::type O16;   // 16-bit outputs share the operands' 16-bit format
   if (a.epi == EPI_STORE) {
-    if constexpr (sizeof(InT) == 2 && BLOCK_N >= 128) {
-      if (a.out_bf16 && a.qkn_gamma) return launch_tc<InT, BLOCK_N, EPI_STORE, O16, false, CTAS, true>(a, s);
-    }
-    if constexpr (sizeof(InT) == 2) {   // K/V-cache rows of head_dim 32: 32-column (64-byte) stores
+    if constexpr (sizeof(InT) == 2) {   // head_dim 32: 32-column (64-byte) staging / K/V-cache lines, per-chunk qk-LN
+      if (a.out_bf16 && a.qkn_gamma && a.qkn_hd == EPI_COLS)
+        return launch_tc<InT, BLOCK_N, EPI_STORE, O16, false, CTAS, true, true>(a, s);
       if (a.out_bf16 && a.kv_k && a.kv_hd == EPI_COLS)
         return launch_tc<InT, BLOCK_N, EPI_STORE, O16, false, CTAS, false, true>(a, s);
+    }
+    if constexpr (sizeof(InT) == 2 && BLOCK_N >= 128) {
+      if (a.out_bf16 && a.qkn_gamma) return launch_tc<InT, BLOCK_N, EPI_STORE, O16, false, CTAS, true>(a, s);
     }
     return a.out_bf16 ? launch_tc<InT, BLOCK_N, EPI_STORE, O16, false, CTAS>(a, s)
                       : launch_tc<InT, BLOCK_N, EPI_STORE, float, false, CTAS>(a, s);
@@ -953,9 +979,9 @@ int linear_forward(const LinearArgs& a, cudaStream_t stream) {
   }
   if (a.qkn_gamma) {
     GN_REQUIRE(a.qkn_beta && a.epi == EPI_STORE && a.in_bf16 && a.out_bf16 && !a.force_simt && !a.conv &&
-                   a.qkn_cols > 0 && a.qkn_cols % (2 * EPI_COLS) == 0 && a.qkn_cols <= a.N && a.N % 128 == 0 &&
-                   !a.ln_stats,
-               "qk-LayerNorm epilogue: bf16 store epilogue on the tensor path, head_dim 64, N %% 128 == 0");
+                   (a.qkn_hd == 2 * EPI_COLS || a.qkn_hd == EPI_COLS) && a.qkn_cols > 0 && a.qkn_cols % a.qkn_hd == 0 &&
+                   a.qkn_cols <= a.N && (a.qkn_hd == EPI_COLS || a.N % 128 == 0) && !a.ln_stats,
+               "qk-LayerNorm epilogue: 16-bit store epilogue on the tensor path, head_dim 64 (N %% 128 == 0) or 32");
   }
   const bool tc_ok = !a.force_simt && (a.N % 64 == 0) && (a.K * esz % 16 == 0) && (a.lda * esz % 16 == 0) &&
                      (a.ldw * esz % 16 == 0) && (a.ldo * (a.out_bf16 ? 2 : 4) % 16 == 0) &&

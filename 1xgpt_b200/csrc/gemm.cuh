@@ -51,6 +51,7 @@ struct LinearArgs {
   const float* qkn_gamma;
   const float* qkn_beta;
   int qkn_cols;
+  int qkn_hd;         // head_dim of the normalised groups: 64 (a pair of 32-column chunks) or 32 (one chunk)
   int a_evict_first;  // 1: A is not read again after this GEMM (L2 evict_first hint on its loads)
   int red_add;        // 1 (EPI_STORE, fp32 out, tensor path): out += A.W^T + bias through TMA reduce-add (the residual
                       // update x += f(x) without loading x into the SM; bit-identical to EPI_RESID in place)

@@ -252,6 +252,7 @@ int linear(gn_model* m, const void* A, int64_t lda, const void* W, int K, const 
   la.red_add = red_add ? 1 : 0;
   if (qkn && m->qkn_epi) {   // q and k columns [0, 2d) get LayerNorm(head_dim) with the attention's shared affine
     la.qkn_gamma = qkn->norm_g; la.qkn_beta = qkn->norm_b; la.qkn_cols = 2 * m->cfg.d_model;
+    la.qkn_hd = m->cfg.d_model / m->cfg.num_heads;
   }
   if (kv && kv->k) {
     la.kv_k = kv->k; la.kv_v = kv->v; la.kv_d = m->cfg.d_model; la.kv_hd = m->cfg.d_model / m->cfg.num_heads;
@@ -788,8 +789,9 @@ int gn_model_create(gn_model** out, const gn_config* cfg, int device) {
     probe.act_bf16 = m->act_bf16; probe.fp16 = m->fp16; probe.n_heads = cfg->num_heads; probe.head_dim = cfg->d_model / cfg->num_heads;
     const char* q = getenv("GENIE_B200_QKN_EPI");   // 0: keep qk-LayerNorm inside the (mma.sync) attention kernels
     const bool qon = !(q && (q[0] == '0' || q[0] == 'n' || q[0] == 'N'));
-    m->qkn_epi = (qon && cfg->qk_norm && m->act_bf16 && !cfg->generic_attention && probe.head_dim == 64 &&
-                  (3 * cfg->d_model) % 128 == 0) ? 1 : 0;
+    m->qkn_epi = (qon && cfg->qk_norm && m->act_bf16 && !cfg->generic_attention &&
+                  ((probe.head_dim == 64 && (3 * cfg->d_model) % 128 == 0) ||
+                   (probe.head_dim == 32 && (3 * cfg->d_model) % 64 == 0))) ? 1 : 0;
     m->tv2 = (on && (!cfg->qk_norm || m->qkn_epi) && !cfg->generic_attention &&
               temporal_v2_supported(probe, cfg->S, cfg->T)) ? 1 : 0;
   }

@@ -600,3 +600,32 @@ def test_fused_readout_sample_matches_two_kernel_path(name, precision, monkeypat
     assert torch.equal(res["1"][0], res["0"][0])
     assert torch.equal(res["1"][3], res["0"][3])
     assert float((res["1"][2] == res["0"][2]).float().mean()) >= 0.99
+
+
+def test_head_dim_32_with_qk_norm():
+    """head_dim 32 with the reference's GenieConfig defaults (qk_norm=True, muP): qk-LayerNorm over 32-column heads in the
+    QKV GEMM epilogue (narrow staging), head-pair tcgen05 spatial attention, 64-byte-line temporal K/V caches - against
+    the CPU oracle, with zero fallback launches, cached == dense."""
+    kw = dict(num_layers=2, num_heads=8, d_model=256, T=16, S=256, image_vocab_size=262144, num_factored_vocabs=2,
+              qk_norm=True, use_mup=True)
+    cfg = O.OracleConfig(**kw)
+    sd = O.init_state_dict(cfg, seed=45, bias_std=0.02)
+    ids = O.synthetic_clips(cfg, 2, seed=46)
+    ids[:, 12:] = cfg.mask_token_id
+    ref = O.compute_logits(sd, cfg, ids)
+    lib = importlib.import_module("1xgpt_b200")._lib.load()
+    for precision, tol in (("fp16", BAR), ("bf16", 6e-3)):
+        m = build_b200_model(kw, sd, precision=precision)
+        f0 = lib.gn_fallback_launches()
+        err = rel_fro(m.compute_logits(ids.cuda()), ref)
+        print(f"hd32 qk_norm {precision}: rel {err:.3e}")
+        assert err < tol
+        assert lib.gn_fallback_launches() == f0
+    noise = O.tie_free_noise(3, 2, cfg.S, seed=47)
+    outs = []
+    for kv in (False, True):
+        m = build_b200_model(kw, sd, precision="fp16", kv_cache=kv)
+        p = ids.clone().cuda()
+        s, _ = m.maskgit_generate(p, 12, maskgit_steps=3, temperature=0.0, noise=noise)
+        outs.append(s.cpu())
+    assert torch.equal(outs[0], outs[1])

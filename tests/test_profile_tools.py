@@ -34,3 +34,28 @@ def test_launch_share_table_reproducible(tmp_path):
     for ln in rows[:8]:                      # the kernels that carry the step
         assert ln in committed, ln
     assert "tcgen05 GEMM variants together 66.1%" in r.stdout
+
+
+def test_round2_ncu_evidence_reproducible(tmp_path):
+    """round 2: the per-kernel table (HBM GB/s and tensor-pipe activity of EVERY kernel family, profiles/r02_ncu_kernels)
+    and bench.py's roofline.traffic source are regenerated from the committed raw ncu pages."""
+    raws = sorted(os.path.join(PROF, "r02_ncu", f) for f in os.listdir(os.path.join(PROF, "r02_ncu")) if f.endswith("_raw.csv.gz"))
+    assert len(raws) >= 8
+    subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), str(tmp_path / "k")] + raws, check=True,
+                   capture_output=True)
+    new = json.load(open(tmp_path / "k.json"))
+    ref = json.load(open(os.path.join(PROF, "r02_ncu_kernels.json")))
+    assert [k["kernel"] for k in new["kernels"]] == [k["kernel"] for k in ref["kernels"]]
+    names = " ".join(k["kernel"] for k in new["kernels"])
+    for fam in ("gemm_tcgen05_kernel", "spatial_attn_tc_persistent_kernel", "temporal_attn_v2_kernel", "prep_kernel",
+                "embed_kernel", "readout_sample_kernel", "remask_kernel", "ce_kernel", "count_equal_kernel",
+                "gn_partial_kernel", "gn_apply_swish_kernel", "stem_conv_kernel", "vq_head_kernel"):
+        assert fam in names, fam
+    for k in new["kernels"]:
+        assert k["avg_us"] > 0 and k["hbm_gbs"] >= 0
+    with gzip.open(os.path.join(PROF, "r02_ncu", "r02_gemm_insitu_raw.csv.gz"), "rt") as f:
+        (tmp_path / "g.csv").write_text(f.read())
+    subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "make_insitu_traffic.py"), str(tmp_path / "g.csv"),
+                    str(tmp_path / "t.json"), "test"], check=True, capture_output=True)
+    t_new, t_ref = json.load(open(tmp_path / "t.json")), json.load(open(os.path.join(PROF, "r02_gemm_insitu_traffic.json")))
+    assert abs(t_new["avg_dram_bytes_per_gemm_launch"] - t_ref["avg_dram_bytes_per_gemm_launch"]) < 1.0
