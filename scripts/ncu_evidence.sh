@@ -23,6 +23,10 @@ cap r02_decode "embed_kernel|readout_sample|remask_kernel|fill_i32|sample_kernel
 cap r02_eval "ce_kernel|count_equal|check_masked|logits_transpose|relevant_weight|readout_sample" 4 8 python scripts/bench_eval.py 8
 cap r02_vq "stem_conv|gn_partial|gn_apply|depth_to_space|vq_head|vq_tail|out_conv" 150 28 python scripts/bench_magvit.py 8
 cap r02_vq_conv gemm_tcgen05 150 6 python scripts/bench_magvit.py 8
+cap r02_vq_extra "depth_to_space|vq_tail|out_conv" 4 6 python scripts/bench_magvit.py 8
+# kernels the bench step / evaluate script do not launch (maskgit_generate's precondition check and logits layout,
+# forward's relevant-position weights, the temperature > 0 sampler)
+cap r02_extra "check_masked|logits_transpose|relevant_weight|sample_kernel|fill_i32|::ce_kernel" 6 10 python scripts/ncu_extra_driver.py
 timeout -k 10 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file $D/r02_launches.csv python scripts/one_step.py 64 > $D/launches.log 2>&1; echo "launch list rc=$?"
 gzip -f $D/r02_launches.csv
 ls -la $D; du -sh gpurun_out

@@ -50,6 +50,8 @@ def main():
             if len(r) < len(hdr):
                 continue
             k = short(r[idx["Kernel Name"]])
+            if k.startswith("at::"):       # torch helper kernels that happened to match a capture regex
+                continue
             us = val(r, "gpu__time_duration.sum", TIME)
             rd, wr = val(r, "dram__bytes_read.sum", UNIT) or 0.0, val(r, "dram__bytes_write.sum", UNIT) or 0.0
             a = agg.setdefault(k, {"n": 0, "us": 0.0, "bytes": 0.0, "tensor": 0.0, "dram_pct": 0.0, "src": os.path.basename(path)})
