@@ -31,7 +31,14 @@ def test_library_exports_every_declared_symbol():
 def test_python_binding_covers_header():
     pkg = importlib.import_module("1xgpt_b200")
     assert sorted(pkg._lib.SIGNATURES) == header_functions()
-    assert pkg._lib.load().gn_version() == 3
+    hdr = open(os.path.join(ROOT, "include", "genie_b200.h")).read()
+    assert pkg._lib.load().gn_version() == int(re.search(r"#define GN_ABI_VERSION (\d+)", hdr).group(1)) == 4
+    # struct mirrors: one ctypes field per C struct member (gn_config / gn_vq_config are passed by pointer)
+    for cname, cls in (("gn_config", pkg._lib.gn_config), ("gn_vq_config", pkg._lib.gn_vq_config)):
+        body = re.search(r"typedef struct " + cname + r" \{(.*?)\} " + cname + ";", re.sub(r"/\*.*?\*/", "", hdr, flags=re.S),
+                         re.S).group(1)
+        members = re.findall(r"\b(?:int32_t|float)\s+([A-Za-z_0-9]+)", body)
+        assert members == [f[0] for f in cls._fields_], (cname, members)
 
 
 def test_no_torch_types_in_abi():
