@@ -1,6 +1,7 @@
 """On-disk token format of the reference (data.py:17-106): `video.bin` (uint32 [num_images, s, s]), optional
 `segment_ids.bin` (int32 [num_images]) and `metadata.json` (keys num_images, s, vocab_size, hz, token_dtype).
-Host-side I/O only: windows of `window_size` frames taken every `stride` frames, windows that
+The training-side `get_maskgit_collator` (data.py:109-169, MaskGIT corruption noise for train.py) is out of scope: this
+path is inference-only.  Host-side I/O only: windows of `window_size` frames taken every `stride` frames, windows that
 straddle two segments dropped (`filter_interrupts`), optional de-overlapping (`filter_overlaps`)."""
 from __future__ import annotations
 
