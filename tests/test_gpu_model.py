@@ -629,3 +629,27 @@ def test_head_dim_32_with_qk_norm():
         s, _ = m.maskgit_generate(p, 12, maskgit_steps=3, temperature=0.0, noise=noise)
         outs.append(s.cpu())
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("vocab,nv", [(65536, 2), (262144, 3), (4096, 1)])
+def test_other_vocab_factorisations_match_oracle(vocab, nv):
+    """GenieConfig allows any image_vocab_size = V ** num_factored_vocabs (config.py:19-20,54-55).  V != 512 takes the
+    two-kernel decode path (readout GEMM + sample_kernel) instead of the fused readout kernel; ids must still equal the
+    oracle's in fp32 mode and the fp16 logits must meet the bar."""
+    kw = dict(num_layers=2, num_heads=4, d_model=128, T=4, S=16, image_vocab_size=vocab, num_factored_vocabs=nv,
+              qk_norm=False, use_mup=False)
+    cfg = O.OracleConfig(**kw)
+    sd = O.init_state_dict(cfg, seed=91, readout_gain=4.0, bias_std=0.02)
+    ids = O.synthetic_clips(cfg, 2, seed=92)
+    ids[:, 2:] = cfg.mask_token_id
+    noise = O.tie_free_noise(3, 2, cfg.S, seed=93)
+    p_ref = ids.clone()
+    s_ref, l_ref = O.maskgit_generate(sd, cfg, p_ref, 2, 3, 0.0, noise=noise)
+    m = build_b200_model(kw, sd, precision="fp32", kv_cache=True)
+    p = ids.clone().cuda()
+    s, fl = m.maskgit_generate(p, 2, maskgit_steps=3, temperature=0.0, noise=noise)
+    assert torch.equal(s.cpu(), s_ref) and torch.equal(p.cpu(), p_ref)
+    assert rel_fro(fl, l_ref) < 2e-5
+    m16 = build_b200_model(kw, sd, precision="fp16", kv_cache=True)
+    _, fl16 = m16.maskgit_generate(ids.clone().cuda(), 2, maskgit_steps=3, temperature=0.0, noise=noise)
+    assert rel_fro(fl16, l_ref) < BAR
