@@ -347,10 +347,11 @@ struct L2WindowScope {
       probed[di] = true;
       setaside = 0;
       max_window_bytes = 0;
-      // MB of L2 set aside for the residual stream (0 = off).  Measured on B200 (126 MB L2): 48 MB +1.7 % frames/s,
-      // 64 MB and more lose (the wide GEMMs then miss on their operands)
+      // MB of L2 set aside for the residual stream (0 = off).  Measured on B200 (126 MB L2), round 2 (fp16 operands,
+      // reduce-add residual epilogue; 3 runs each, same box): 0 / 8 / 16 / 24 / 32 / 40 / 48 MB = 1908 / 1934 / 1945 /
+      // 1949-1958 / 1952 / 1943 / 1935 frames/s; 64 MB and more lose 8-15 % (the wide GEMMs then miss on their operands)
       const char* e = getenv("GENIE_B200_L2_PERSIST");
-      const int64_t want = (int64_t)(e ? atoi(e) : 48) << 20;
+      const int64_t want = (int64_t)(e ? atoi(e) : 24) << 20;
       int dev = 0, max_persist = 0, max_window = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
@@ -368,6 +369,7 @@ struct L2WindowScope {
     if (setaside <= 0 || m->x == nullptr) return;
     // the window may not exceed cudaDevAttrMaxAccessPolicyWindowSize (128 MB on B200): larger chunks keep the policy
     // on their first rows only (a launch with a larger window fails with cudaErrorInvalidValue)
+    // (a window over the first `setaside` bytes only, hitRatio 1, measured the same as a random fraction of all rows)
     const int64_t bytes = std::min<int64_t>(n_rows * m->cfg.d_model * 4, max_window_bytes);
     g_l2_window.base_ptr = m->x;
     g_l2_window.num_bytes = (size_t)bytes;
