@@ -2,6 +2,7 @@
 // LayerNorm / cast "prep" that feeds the GEMM A operand, frame gather for the readout.
 // One warp per token row, 16-byte accesses, fp32 statistics via warp shuffles.
 #include "kernels.cuh"
+#include <cmath>
 #include <type_traits>
 
 namespace gn {
@@ -134,17 +135,21 @@ prep_kernel(const float* __restrict__ x, OutT* __restrict__ out, const float* __
 template <typename OutT>
 static int launch_prep_t(const float* x, OutT* out, const float* gamma, const float* beta, int n_rows, int d,
                          float scale, int S, int Tact, int tsel, cudaStream_t st, int round_tf32) {
+  // 8 warps (= rows) per block.  (Capping the resident blocks so that the last wave is full - 7 blocks per SM give
+  // 3.95 / 1.98 waves instead of 3.46 / 1.73 at the 32768 / 16384 rows of a decode step - was measured SLOWER: LayerNorm
+  // passes 22.7 -> 24.7 ms per step; the pass wants every resident warp it can get.)
   const int wpb = 8;
+  const size_t pad = 0;
   const int grid = ceil_div(n_rows, wpb);
   const int nvec = d / 4;
   if (nvec <= 32 * 2)
-    GN_CUDA_CHECK(launch_kernel(PC_PREP, prep_kernel<OutT, 2>, dim3(grid), dim3(wpb * 32), 0, st, x, out, gamma, beta, n_rows, d, 1e-5f, scale, S, Tact, tsel, round_tf32));
+    GN_CUDA_CHECK(launch_kernel(PC_PREP, prep_kernel<OutT, 2>, dim3(grid), dim3(wpb * 32), pad, st, x, out, gamma, beta, n_rows, d, 1e-5f, scale, S, Tact, tsel, round_tf32));
   else if (nvec <= 32 * 4)
-    GN_CUDA_CHECK(launch_kernel(PC_PREP, prep_kernel<OutT, 4>, dim3(grid), dim3(wpb * 32), 0, st, x, out, gamma, beta, n_rows, d, 1e-5f, scale, S, Tact, tsel, round_tf32));
+    GN_CUDA_CHECK(launch_kernel(PC_PREP, prep_kernel<OutT, 4>, dim3(grid), dim3(wpb * 32), pad, st, x, out, gamma, beta, n_rows, d, 1e-5f, scale, S, Tact, tsel, round_tf32));
   else if (nvec <= 32 * 8)
-    GN_CUDA_CHECK(launch_kernel(PC_PREP, prep_kernel<OutT, 8>, dim3(grid), dim3(wpb * 32), 0, st, x, out, gamma, beta, n_rows, d, 1e-5f, scale, S, Tact, tsel, round_tf32));
+    GN_CUDA_CHECK(launch_kernel(PC_PREP, prep_kernel<OutT, 8>, dim3(grid), dim3(wpb * 32), pad, st, x, out, gamma, beta, n_rows, d, 1e-5f, scale, S, Tact, tsel, round_tf32));
   else if (nvec <= 32 * 16)
-    GN_CUDA_CHECK(launch_kernel(PC_PREP, prep_kernel<OutT, 16>, dim3(grid), dim3(wpb * 32), 0, st, x, out, gamma, beta, n_rows, d, 1e-5f, scale, S, Tact, tsel, round_tf32));
+    GN_CUDA_CHECK(launch_kernel(PC_PREP, prep_kernel<OutT, 16>, dim3(grid), dim3(wpb * 32), pad, st, x, out, gamma, beta, n_rows, d, 1e-5f, scale, S, Tact, tsel, round_tf32));
   else {
     set_error("prep: d_model %d > 2048 not supported", d);
     return GN_ERR_UNSUPPORTED;
