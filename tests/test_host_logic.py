@@ -198,3 +198,25 @@ def test_magvit2_lightning_checkpoint_loader(golden_dir):
         torch.save({"state_dict": broken}, os.path.join(td, "b.ckpt"))
         with pytest.raises(KeyError):
             pkg.VQModel.from_ckpt(os.path.join(td, "b.ckpt"), cfg)
+
+
+def test_product_package_never_touches_the_oracle_or_the_reference():
+    """oracle/ is test infrastructure: the shipped package must not import, open or mention a path into it (nor into
+    /root/reference, which does not exist on the GPU box); bench.py may use it only in its CPU legs."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    paths = glob.glob(os.path.join(root, "1xgpt_b200", "**", "*.py"), recursive=True)
+    paths += glob.glob(os.path.join(root, "1xgpt_b200", "csrc", "*"))
+    for path in paths:
+        if os.path.isdir(path):
+            continue
+        src = open(path, errors="ignore").read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), path
+        if path.endswith(".py"):
+            assert "/root/reference" not in src, path
+    bench = open(os.path.join(root, "bench.py")).read()
+    for m in re.finditer(r"from oracle import", bench):
+        before = bench[:m.start()]
+        fn = re.findall(r"^def (\w+)\(", before, re.M)[-1]
+        assert fn in ("oracle_config", "pick_cpu_threads", "cpu_generate_sample", "run_reference"), fn
