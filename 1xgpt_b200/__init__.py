@@ -17,11 +17,15 @@ from .model import (  # noqa: E402
 )
 from .vq import VQModel, VQConfig, decode_latents_wrapper  # noqa: E402
 from .synth import synthetic_state_dict  # noqa: E402
+from .eval_utils import AvgMetric, compute_loss, decode_tokens  # noqa: E402
+from .evaluate import GenieEvaluator  # noqa: E402
+from .data import RawTokenDataset, get_maskgit_collator  # noqa: E402
 from .factorization_utils import factorize_token_ids, unfactorize_token_ids, factorize_labels, nth_root  # noqa: E402
 
 __all__ = [
     "GenieConfig", "STMaskGIT", "STTransformerDecoder", "STBlock", "Mlp", "SelfAttention", "BasicSelfAttention",
     "MemoryEfficientAttention", "FactorizedEmbedding", "ModelOutput", "cosine_schedule", "factorize_token_ids",
     "unfactorize_token_ids", "factorize_labels", "nth_root", "GnError", "VQModel", "VQConfig", "decode_latents_wrapper",
-    "synthetic_state_dict",
+    "synthetic_state_dict", "AvgMetric", "compute_loss", "decode_tokens", "GenieEvaluator", "RawTokenDataset",
+    "get_maskgit_collator",
 ]

@@ -57,4 +57,4 @@ class GenieConfig:
         self.factored_vocab_size = nth_root(self.image_vocab_size, self.num_factored_vocabs)
         # attn_drop / mlp_drop are accepted and ignored: dropout is the identity in eval mode, and this path is
         # inference-only (the reference loads such checkpoints for generate.py / evaluate.py too).  Training
-        # (train.py, data.get_maskgit_collator) is out of scope: SURVEY.md section 2 rows 9 and 16.
+        # (train.py) is out of scope: SURVEY.md section 2 row 9.

@@ -7,6 +7,7 @@
 #include "kernels.cuh"
 #include "vq_kernels.cuh"
 #include "../../include/genie_b200.h"
+#include <cstdlib>
 #include <map>
 #include <set>
 #include <string>
@@ -56,6 +57,7 @@ struct gn_vq {
   void* a = nullptr;     // convolution operand (GroupNorm + swish output / cast trunk) in the operand format
   double* stats = nullptr;
   int o16 = 2;           // operand format: 2 = fp16 (default), 1 = bf16, 0 = fp32 on the CUDA-core kernels (exact mode)
+  int per = 8;           // images per pass through the trunk (GENIE_B200_VQ_PER; workspace = per x ~120 MB at 256x256)
   size_t esz() const { return o16 ? 2 : 4; }
 };
 
@@ -200,6 +202,15 @@ int gn_vq_create(gn_vq** out, const gn_vq_config* cfg, int device) {
              "MAGVIT2 path: precision must be GN_PREC_FP16, GN_PREC_BF16 or GN_PREC_FP32 (got %d)", cfg->precision);
   m->o16 = cfg->precision == GN_PREC_FP16 ? 2 : (cfg->precision == GN_PREC_BF16 ? 1 : 0);
   m->nb = cfg->num_blocks;
+  {
+    // Images per pass.  The coarse levels of a pass are small GEMMs (16x16 latents: 256 rows per image), so more images
+    // per pass fill the 148 SMs better there; the fine levels no longer fit L2 either way (33 MB fp32 per image at
+    // 256x256x128).  Results do not depend on it (every kernel treats images independently; GroupNorm statistics are
+    // per image in a fixed order).
+    const char* e = getenv("GENIE_B200_VQ_PER");
+    const int v = e ? atoi(e) : 0;
+    if (v >= 1 && v <= 64) m->per = v;
+  }
   for (int i = 0; i < m->nb; ++i) m->ch.push_back(cfg->base_channels * cfg->ch_mult[i]);
   m->enc_down.assign(m->nb, std::vector<ResW>(cfg->num_res_blocks));
   m->enc_ds.resize(m->nb);
@@ -295,7 +306,7 @@ int gn_vq_encode(gn_vq* m, const float* img, int B, int H, int W, int32_t* ids, 
   GN_REQUIRE(H % down == 0 && W % down == 0, "image %dx%d must be a multiple of %d", H, W, down);
   VqGuard g(m->device);
   cudaStream_t st = (cudaStream_t)stream;
-  const int per = 8;  // images per pass (workspace bound)
+  const int per = m->per;  // images per pass (workspace bound)
   for (int b0 = 0; b0 < B; b0 += per) {
     const int n = std::min(per, B - b0);
     GN_PROPAGATE(ensure_ws(m, per, H, W));
@@ -329,7 +340,7 @@ int gn_vq_decode(gn_vq* m, const int32_t* ids, int B, int h0, int w0, int little
   cudaStream_t st = (cudaStream_t)stream;
   const int nb = m->nb, up = 1 << (nb - 1);
   const int H = h0 * up, W = w0 * up;
-  const int per = 8;
+  const int per = m->per;
   for (int b0 = 0; b0 < B; b0 += per) {
     const int n = std::min(per, B - b0);
     GN_PROPAGATE(ensure_ws(m, per, H, W));

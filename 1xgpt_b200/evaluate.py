@@ -89,3 +89,54 @@ def b200_backend(model, maskgit_steps: int = 2, unmask_mode: str = "random", noi
                                          noise=noise, temperature=temperature, uniform=uniform)
 
     return fn
+
+
+class GenieEvaluator:
+    """Drop-in for genie/evaluate.py:68-143: `args` carries `checkpoint_dir`, `maskgit_steps`, `temperature`,
+    `latent_h`, `latent_w` (the reference's argparse namespace); `decode_latents` is an instance of
+    `decode_latents_wrapper()`.  `model=` hands over an already constructed 1xgpt_b200.STMaskGIT instead of loading
+    `args.checkpoint_dir` (extra keyword arguments go to `STMaskGIT.from_pretrained`, e.g. precision / kv_cache).
+
+    `predict_zframe_logits` is the reference's loop, one `maskgit_generate` per timestep (evaluate.py:103-122), for
+    callers that want the samples and the factored logits; the metric loop of the CLI uses the fused
+    `teacher_forced_eval` (`b200_backend` above), which never materialises the logits."""
+
+    def __init__(self, args, decode_latents=None, device="cuda", model=None, **model_kwargs):
+        from .model import STMaskGIT
+        if model is None:
+            model_kwargs.setdefault("kv_cache", True)
+            model = STMaskGIT.from_pretrained(args.checkpoint_dir, **model_kwargs)
+        self.model = model.to(device=device)
+        self.model.eval()
+        self.decode_latents = decode_latents
+        self.device = device
+        self.args = args
+
+    @torch.no_grad()
+    def predict_zframe_logits(self, input_ids: torch.LongTensor, noise: Optional[torch.Tensor] = None):
+        """input_ids (B, T*H*W) -> (samples_THW (B, T-1, H, W), factored_logits (B, V, NV, T-1, H, W)).
+        `noise` [T-1, K-1, B, S] optionally fixes the MaskGIT re-mask noise (torch.rand_like in the reference)."""
+        cfg = self.model.config
+        B = input_ids.size(0)
+        window = cfg.T
+        h, w = int(self.args.latent_h), int(self.args.latent_w)
+        inputs_THW = input_ids.reshape(B, window, h, w).to(self.device)
+        steps = int(self.args.maskgit_steps)
+        all_samples, all_logits = [], []
+        for timestep in range(1, window):
+            inputs_masked = inputs_THW.clone()
+            inputs_masked[:, timestep:] = self.model.mask_token_id
+            samples_HW, factored_logits = self.model.maskgit_generate(
+                inputs_masked, out_t=timestep, maskgit_steps=steps, temperature=float(self.args.temperature),
+                noise=None if noise is None else noise[timestep - 1])
+            all_samples.append(samples_HW)
+            all_logits.append(factored_logits)
+        return torch.stack(all_samples, dim=1), torch.stack(all_logits, dim=3)
+
+    @torch.no_grad()
+    def predict_next_frames(self, samples_THW) -> torch.Tensor:
+        """samples (B, T-1, H, W) -> uint8 frames (B, T-1, 3, 16H, 16W) through the MAGVIT2 decoder (evaluate.py:124-143)."""
+        from .eval_utils import decode_tokens
+        if self.decode_latents is None:
+            raise ValueError("GenieEvaluator was built without decode_latents (decode_latents_wrapper(...))")
+        return decode_tokens(samples_THW.cpu(), self.decode_latents)

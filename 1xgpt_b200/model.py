@@ -474,6 +474,27 @@ class STMaskGIT(nn.Module):
         return ModelOutput(loss=loss, acc=accuracy, logits=logits)
 
     @torch.no_grad()
+    def compute_loss_and_acc(self, logits_CTHW, targets_THW, relevant_mask_THW):
+        """st_mask_git.py:231-253: mean CE (summed over the factored vocabularies) and all-vocabularies-correct
+        accuracy over the positions of frames 1.. where `relevant_mask_THW` ([B, T-1, H, W], frames 1..) is set.  `forward`
+        fuses this with the readout; this stand-alone form runs the same CE kernel on caller-supplied logits
+        [B, NV*V, T, H, W]."""
+        from .eval_utils import factored_cross_entropy
+        c = self.config
+        Cc = c.factored_vocab_size * c.num_factored_vocabs
+        B, T = targets_THW.shape[0], targets_THW.shape[1]
+        if logits_CTHW.shape[0] != B or logits_CTHW.shape[1] != Cc or logits_CTHW.shape[2] != T:
+            raise ValueError(f"expected logits [B,{Cc},T,H,W] matching targets [B,T,H,W], got "
+                             f"{tuple(logits_CTHW.shape)} vs {tuple(targets_THW.shape)}")
+        tg = self._ids32(targets_THW[:, 1:].reshape(B, -1), labels=True)
+        rows = logits_CTHW.to(self.device)[:, :, 1:].permute(0, 2, 3, 4, 1).reshape(-1, Cc)
+        if tuple(relevant_mask_THW.shape[:2]) != (B, T - 1):
+            raise ValueError(f"relevant_mask_THW must cover frames 1..: [B,{T - 1},H,W], got {tuple(relevant_mask_THW.shape)}")
+        w = relevant_mask_THW.to(self.device).reshape(-1)
+        acc = factored_cross_entropy(rows, tg.reshape(-1), c.num_factored_vocabs, c.factored_vocab_size, weight=w)
+        return (acc[0] / acc[1]).to(torch.float32), (acc[2] / acc[1]).to(torch.float32)
+
+    @torch.no_grad()
     def teacher_forced_eval(self, input_ids: torch.Tensor, maskgit_steps: int = 2, unmask_mode: str = "random",
                             noise: Optional[torch.Tensor] = None, return_samples: bool = False,
                             temperature: float = 0.0, uniform: Optional[torch.Tensor] = None):

@@ -653,3 +653,49 @@ def test_other_vocab_factorisations_match_oracle(vocab, nv):
     m16 = build_b200_model(kw, sd, precision="fp16", kv_cache=True)
     _, fl16 = m16.maskgit_generate(ids.clone().cuda(), 2, maskgit_steps=3, temperature=0.0, noise=noise)
     assert rel_fro(fl16, l_ref) < BAR
+
+
+@pytest.mark.parametrize("name", TINY)
+def test_eval_utils_compute_loss_and_evaluator_match_reference(name):
+    """eval_utils.compute_loss (eval_utils.py:44-77) on reference logits vs the reference's own number; STMaskGIT.
+    compute_loss_and_acc (st_mask_git.py:231-253) vs the reference's forward loss / acc; GenieEvaluator.
+    predict_zframe_logits (evaluate.py:82-122) + compute_loss vs the oracle's teacher-forced loop (samples bit-exact)."""
+    import types
+    g = importlib.import_module("1xgpt_b200")
+    z = load_golden(name)
+    kw, sd = golden_cfg(z), golden_sd(z)
+    cfg = O.OracleConfig(**kw)
+    ids = torch.from_numpy(z["ids"])
+    B = ids.shape[0]
+    NV, V = cfg.num_factored_vocabs, cfg.factored_vocab_size
+    # 1. the reference's logits -> our compute_loss == the reference's compute_loss (device and host logits alike)
+    logits = torch.from_numpy(z["logits"])
+    fl = logits[:, :, 1:].reshape(B, NV, V, cfg.T - 1, cfg.hw, cfg.hw).transpose(1, 2)
+    for dev in ("cuda", "cpu"):
+        loss = g.compute_loss(ids.reshape(B, -1), fl.to(dev), NV, V)
+        assert abs(loss - float(z["eval_loss"])) < 1e-4, (dev, loss)
+    # 2. compute_loss_and_acc on the reference's logits and the MLM mask of the forward fixture
+    m = build_b200_model(kw, sd, precision="fp32")
+    x_in = torch.from_numpy(z["fwd_in"]).reshape(B, cfg.T, cfg.hw, cfg.hw)
+    ref_logits = O.compute_logits(sd, cfg, x_in).reshape(B, NV * V, cfg.T, cfg.hw, cfg.hw)
+    relevant = x_in[:, 1:] == cfg.mask_token_id
+    loss, acc = m.compute_loss_and_acc(ref_logits.cuda(), ids.reshape(B, cfg.T, cfg.hw, cfg.hw).cuda(), relevant.cuda())
+    assert abs(float(loss) - float(z["fwd_loss"])) < 1e-4 and abs(float(acc) - float(z["fwd_acc"])) < 1e-7
+    out = m(x_in.reshape(B, -1).cuda(), ids.reshape(B, -1).cuda())
+    loss2, acc2 = m.compute_loss_and_acc(out.logits, ids.reshape(B, cfg.T, cfg.hw, cfg.hw), relevant)
+    assert abs(float(loss2) - float(out.loss)) < 1e-6 and float(acc2) == float(out.acc)
+    with pytest.raises(ValueError):
+        m.compute_loss_and_acc(out.logits, ids.reshape(B, cfg.T, cfg.hw, cfg.hw), x_in == cfg.mask_token_id)
+    # 3. the evaluator's per-timestep loop vs the oracle
+    noise = torch.stack([O.tie_free_noise(2, B, cfg.S, seed=900 + t) for t in range(cfg.T - 1)])
+    o_loss, o_acc, o_samples = O.teacher_forced_metrics(sd, cfg, ids.reshape(B, -1), 2, noise)
+    args = types.SimpleNamespace(checkpoint_dir=None, maskgit_steps=2, temperature=0, latent_h=cfg.hw, latent_w=cfg.hw)
+    for kv in (False, True):
+        ev = g.GenieEvaluator(args, decode_latents=None, model=build_b200_model(kw, sd, precision="fp32", kv_cache=kv))
+        samples, flg = ev.predict_zframe_logits(ids.reshape(B, -1), noise=noise)
+        assert tuple(flg.shape) == (B, V, NV, cfg.T - 1, cfg.hw, cfg.hw)
+        assert torch.equal(samples.cpu(), o_samples)
+        assert abs(g.compute_loss(ids.reshape(B, -1), flg, NV, V) - o_loss) < 1e-4
+        assert abs(float((ids.reshape(B, cfg.T, cfg.hw, cfg.hw)[:, 1:].cuda() == samples).float().mean()) - o_acc) < 1e-9
+        with pytest.raises(ValueError, match="decode_latents"):
+            ev.predict_next_frames(samples)
