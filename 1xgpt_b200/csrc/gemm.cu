@@ -263,7 +263,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // both CTAs' bytes complete on the LEADER's barrier (which the MMA issuer waits on)
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * SM::STAGE_BYTES);
             const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
-            if (a_hint) tma_load_2d_pair_hint(smem_a + stage * A_TILE_BYTES, &tmA, bar, kb * BLOCK_K, m_row0, pol);
+            if (args.cin_blocks > 0) {
+              // conv: this CTA's 128 rows = th x tw output pixels of image n starting at (y0, x0) (same tile geometry
+              // as the single-CTA path; the pair shares the weight tile, each CTA staging one half of it)
+              const int P = args.Ho * args.Wo;
+              const int n = m_row0 / P, rem = m_row0 % P;
+              const int y0 = rem / args.Wo, x0 = rem % args.Wo;
+              const int tap = kb / args.cin_blocks, cib = kb % args.cin_blocks;
+              tma_load_4d_pair(smem_a + stage * A_TILE_BYTES, &tmA, bar, cib * BLOCK_K, x0 * args.stride + tap % 3 - 1,
+                               y0 * args.stride + tap / 3 - 1, n);
+            } else if (a_hint) tma_load_2d_pair_hint(smem_a + stage * A_TILE_BYTES, &tmA, bar, kb * BLOCK_K, m_row0, pol);
             else tma_load_2d_pair(smem_a + stage * A_TILE_BYTES, &tmA, bar, kb * BLOCK_K, m_row0);
             tma_load_2d_pair(smem_b + stage * SM::B_TILE_BYTES, &tmB, bar, kb * BLOCK_K,
                              n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / 2));
@@ -816,6 +825,9 @@ int dispatch_epi(const LinearArgs& a, cudaStream_t s) {
   if (a.epi == EPI_RESID) {
     if (a.out_bf16) { set_error("EPI_RESID writes the fp32 residual stream"); return GN_ERR_INVALID; }
     if constexpr (BLOCK_N <= 128) {
+      if constexpr (CTAS == 2 && BLOCK_N == 128) {   // CTA-pair convolution tiles (256 pixels x 128 channels)
+        if (a.conv && !a.out2) return launch_tc<InT, BLOCK_N, EPI_RESID, float, false, 2>(a, s);
+      }
       return a.out2 ? launch_tc<InT, BLOCK_N, EPI_RESID, float, true>(a, s)
                     : launch_tc<InT, BLOCK_N, EPI_RESID, float, false>(a, s);
     } else {   // 256-wide: 3 residual staging buffers when the bf16 copy is emitted too
@@ -835,6 +847,14 @@ int dispatch_n(const LinearArgs& a, cudaStream_t s) {
   // reads per MMA cycle), so those use 256 with a 3-stage ring.
   // 256-wide tiles run as CTA pairs (256 x 256 per pair, cta_group::2) unless disabled or a convolution
   const bool pair = env_on("GENIE_B200_PAIR", g_use_pair) && !a.conv && a.M > BLOCK_M;
+  // Convolutions (MAGVIT2): CTA-pair tiles of 256 pixels x BLOCK_N channels, each CTA staging its own 128-pixel A box and
+  // half of the weight tile.  The 3x3 convs at Cout = 128 move 16 KB (A) + 16 KB (B) from L2 per 2 MFLOP k-block in the
+  // single-CTA form - twice the L2 -> SM intensity of the K = 512 linear layers, which is what bounds them; the pair
+  // form needs 16 + 8 KB.  GENIE_B200_CONV_PAIR=0 restores single-CTA tiles (A/B).
+  if (a.conv && a.M % (2 * BLOCK_M) == 0 && env_on("GENIE_B200_PAIR", g_use_pair) && env_on("GENIE_B200_CONV_PAIR", false)) {
+    if (a.N % 256 == 0) return dispatch_epi<InT, 256, 2>(a, s);
+    if (a.N % 128 == 0) return dispatch_epi<InT, 128, 2>(a, s);
+  }
   // experiment switch for the N = 512 GEMMs (proj / fc2): GENIE_B200_BN512 = 64 | 128 | 256 (single CTA) | 1128 | 1256
   // (CTA pair with 128 / 256-wide tiles)
   if (a.N == 512 && !a.conv) {

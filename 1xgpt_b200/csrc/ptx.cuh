@@ -288,6 +288,15 @@ __device__ __forceinline__ void tma_load_2d_pair_hint(void* smem_dst, const CUte
       "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_bar_addr), "r"(x), "r"(y), "l"(policy)
       : "memory");
 }
+// 4-D (NHWC convolution) tile load of one CTA of a pair; completes on the LEADER's barrier like tma_load_2d_pair
+__device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const CUtensorMap* m, uint32_t cluster_bar_addr, int c0,
+                                                 int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_bar_addr), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3)
+      : "memory");
+}
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot) {   // one warp in EACH CTA of the pair
   static_assert(NCOLS >= 32 && NCOLS <= 512 && (NCOLS & (NCOLS - 1)) == 0, "TMEM columns: pow2 in [32,512]");

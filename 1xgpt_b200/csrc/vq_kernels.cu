@@ -4,6 +4,7 @@
 // reference: magvit2/modules/diffusionmodules/improved_model.py, magvit2/modules/vqvae/lookup_free_quantize.py
 #include "kernels.cuh"
 #include "vq_kernels.cuh"
+#include <cstdlib>
 
 namespace gn {
 
@@ -11,21 +12,24 @@ namespace gn {
 // stem: conv 3x3 (Cin = 3, padding 1, no bias) from the NCHW fp32 image to the NHWC fp32 trunk
 // improved_model.py:67-73 (Encoder.conv_in).  w: [Cout, 3, 3, 3] (PyTorch OIHW).
 // -------------------------------------------------------------------------------------
-// One block = one image row.  The 3 input rows (3 channels, zero padded) are staged in shared memory; a warp walks 32
-// consecutive pixels with the 3x3x3 window sliding through registers (9 broadcast LDS per pixel), each lane owns
-// Cout/32 output channels with their 27 taps in registers, so a pixel's Cout floats leave the warp as ONE contiguous
-// store (512 B for Cout = 128).  The first version (one thread = 32 channels of one pixel, scalar stores 128 B apart)
-// ran 1.05 ms per 8 images; the trunk it writes is 268 MB = ~45 us of HBM time.
-template <int CPL>   // output channels per lane
+// One block = ROWS consecutive image rows (round 2b; the first TMA-free version took one row per block, so the 108 weight
+// loads per lane, the staging of 3 input rows and the barrier were paid for every 32 pixels a warp produces: 214 us per 8
+// images against ~45 us of HBM time for the 268 MB trunk it writes).  The ROWS + 2 input rows (3 channels, zero padded)
+// are staged in shared memory once; a warp takes (row, 32-pixel segment) items and walks the segment with the 3x3x3
+// window sliding through registers (9 broadcast LDS per pixel); each lane owns Cout/32 output channels with their 27 taps
+// in registers, so a pixel's Cout floats leave the warp as ONE contiguous store (512 B for Cout = 128).  The tap order of
+// the per-pixel sum is unchanged (k = ci*9 + ky*3 + kx), results are bit-identical for every ROWS.
+template <int CPL, int ROWS>   // output channels per lane, image rows per block
 __global__ void __launch_bounds__(256)
 stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w, float* __restrict__ out, int H, int W) {
   constexpr int Cout = CPL * 32;
-  extern __shared__ float srow[];        // [3 ci][3 ky][W + 2]
-  const int n = blockIdx.y, y = blockIdx.x;
+  constexpr int RS = ROWS + 2;           // staged input rows per channel
+  extern __shared__ float srow[];        // [3 ci][ROWS + 2][W + 2]
+  const int n = blockIdx.y, y0 = blockIdx.x * ROWS;
   const int Wp = W + 2;
-  for (int i = threadIdx.x; i < 9 * Wp; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 3 * RS * Wp; i += blockDim.x) {
     const int r = i / Wp, xx = i % Wp - 1;
-    const int ci = r / 3, yy = y + r % 3 - 1;
+    const int ci = r / RS, yy = y0 + r % RS - 1;
     srow[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? img[(((int64_t)n * 3 + ci) * H + yy) * W + xx] : 0.f;
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -35,13 +39,19 @@ stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w, flo
 #pragma unroll
     for (int k = 0; k < 27; ++k) wr[c][k] = __ldg(w + (int64_t)(lane * CPL + c) * 27 + k);
   __syncthreads();
-  float* orow = out + ((int64_t)n * H + y) * W * Cout;
-  for (int x0 = warp * 32; x0 < W; x0 += nwarps * 32) {
+  const int segs = (W + 31) / 32;
+  for (int item = warp; item < ROWS * segs; item += nwarps) {
+    const int ry = item / segs, x0 = (item % segs) * 32;
+    if (y0 + ry >= H) break;             // items are row-major: every later item of this warp is out of range too
+    float* orow = out + ((int64_t)n * H + y0 + ry) * W * Cout;
+    int so[9];                           // offset of the staged input row behind window row r = ci*3 + ky
+#pragma unroll
+    for (int r = 0; r < 9; ++r) so[r] = ((r / 3) * RS + ry + r % 3) * Wp;
     float win[9][3];                     // [ci*3 + ky][kx]
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
-      win[r][1] = srow[r * Wp + x0];     // padded column x0 - 1 + 1
-      win[r][2] = srow[r * Wp + x0 + 1];
+      win[r][1] = srow[so[r] + x0];      // padded column x0 - 1 + 1
+      win[r][2] = srow[so[r] + x0 + 1];
     }
     const int xe = min(x0 + 32, W);
     for (int x = x0; x < xe; ++x) {
@@ -49,7 +59,7 @@ stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w, flo
       for (int r = 0; r < 9; ++r) {
         win[r][0] = win[r][1];
         win[r][1] = win[r][2];
-        win[r][2] = srow[r * Wp + x + 2];
+        win[r][2] = srow[so[r] + x + 2];
       }
       float acc[CPL];
 #pragma unroll
@@ -70,21 +80,31 @@ stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w, flo
   }
 }
 
-int launch_stem_conv(const float* img, const float* w, float* out, int B, int H, int W, int Cout, cudaStream_t st) {
-  GN_REQUIRE(Cout % 32 == 0 && Cout <= 256, "stem conv: Cout %d unsupported", Cout);
-  const size_t smem = (size_t)9 * (W + 2) * sizeof(float);
-  GN_REQUIRE(smem <= 48 * 1024, "stem conv: image width %d too large", W);
-  dim3 grid(H, B);
+template <int ROWS>
+static int launch_stem_rows(const float* img, const float* w, float* out, int B, int H, int W, int Cout, cudaStream_t st) {
+  const size_t smem = (size_t)3 * (ROWS + 2) * (W + 2) * sizeof(float);
+  dim3 grid(ceil_div(H, ROWS), B);
   switch (Cout / 32) {
-    case 1: stem_conv_kernel<1><<<grid, 256, smem, st>>>(img, w, out, H, W); break;
-    case 2: stem_conv_kernel<2><<<grid, 256, smem, st>>>(img, w, out, H, W); break;
-    case 4: stem_conv_kernel<4><<<grid, 256, smem, st>>>(img, w, out, H, W); break;
-    case 8: stem_conv_kernel<8><<<grid, 256, smem, st>>>(img, w, out, H, W); break;
+    case 1: stem_conv_kernel<1, ROWS><<<grid, 256, smem, st>>>(img, w, out, H, W); break;
+    case 2: stem_conv_kernel<2, ROWS><<<grid, 256, smem, st>>>(img, w, out, H, W); break;
+    case 4: stem_conv_kernel<4, ROWS><<<grid, 256, smem, st>>>(img, w, out, H, W); break;
+    case 8: stem_conv_kernel<8, ROWS><<<grid, 256, smem, st>>>(img, w, out, H, W); break;
     default: set_error("stem conv: Cout %d unsupported (32, 64, 128, 256)", Cout); return GN_ERR_UNSUPPORTED;
   }
   GN_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;
   return GN_OK;
+}
+
+int launch_stem_conv(const float* img, const float* w, float* out, int B, int H, int W, int Cout, cudaStream_t st) {
+  GN_REQUIRE(Cout % 32 == 0 && Cout <= 256, "stem conv: Cout %d unsupported", Cout);
+  GN_REQUIRE((size_t)9 * (W + 2) * sizeof(float) <= 48 * 1024, "stem conv: image width %d too large", W);
+  // 8 rows per block when the 10 staged rows fit the default 48 KB of shared memory (W <= 407), else one row per block.
+  // GENIE_B200_STEM_ROWS=1 forces the one-row variant (A/B; results are bit-identical)
+  static const bool one_row = [] { const char* e = getenv("GENIE_B200_STEM_ROWS"); return e && e[0] == '1'; }();
+  if (!one_row && (size_t)3 * 10 * (W + 2) * sizeof(float) <= 48 * 1024)
+    return launch_stem_rows<8>(img, w, out, B, H, W, Cout, st);
+  return launch_stem_rows<1>(img, w, out, B, H, W, Cout, st);
 }
 
 // -------------------------------------------------------------------------------------
