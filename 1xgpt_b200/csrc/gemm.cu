@@ -850,7 +850,10 @@ int dispatch_n(const LinearArgs& a, cudaStream_t s) {
   // Convolutions (MAGVIT2): CTA-pair tiles of 256 pixels x BLOCK_N channels, each CTA staging its own 128-pixel A box and
   // half of the weight tile.  The 3x3 convs at Cout = 128 move 16 KB (A) + 16 KB (B) from L2 per 2 MFLOP k-block in the
   // single-CTA form - twice the L2 -> SM intensity of the K = 512 linear layers, which is what bounds them; the pair
-  // form needs 16 + 8 KB.  GENIE_B200_CONV_PAIR=0 restores single-CTA tiles (A/B).
+  // form needs 16 + 8 KB.  MEASURED AND LEFT OFF (GENIE_B200_CONV_PAIR=1 enables it; tokenizer tests pass with it): the
+  // Cout = 128 convs got slower (ncu: 464 -> 528 us store, 553 -> 602 us residual per launch at 32 images), the Cout >= 256
+  // ones 114 -> 100 us; encode 3187-3241 vs 3161-3171 img/s, decode 2328-2341 vs 2330-2332: the 128-wide conv tiles are
+  // not bound by the L2 -> SM operand stream.
   if (a.conv && a.M % (2 * BLOCK_M) == 0 && env_on("GENIE_B200_PAIR", g_use_pair) && env_on("GENIE_B200_CONV_PAIR", false)) {
     if (a.N % 256 == 0) return dispatch_epi<InT, 256, 2>(a, s);
     if (a.N % 128 == 0) return dispatch_epi<InT, 128, 2>(a, s);

@@ -502,6 +502,146 @@ int launch_out_conv(const void* a, int o16, const float* w, const float* bias, f
   return launch_out_conv_t<float>(static_cast<const float*>(a), w, bias, out_f32, out_u8, B, H, W, C, st);
 }
 
+// -------------------------------------------------------------------------------------
+// decoder output conv on the warp-level tensor cores (16-bit operand modes): 3x3, C -> 3, + bias, as an implicit GEMM
+// with mma.sync m16n8k16 (fp32 accumulate): M = 16 consecutive pixels of one image row, N = 8 (3 used), K = 9 taps x C.
+// The CUDA-core kernel above spends 7x its FMA floor (1.55 ms per 32 images, 6.6 % of an encode + decode pass); here the
+// arithmetic is 72 MMAs per 16 pixels and the kernel is bound by streaming the activation through L1.
+//   * A fragments come straight from global memory (L1-cached; every line is reused by up to 9 taps): K is PERMUTED so
+//     that lane (r = lane / 4, j = lane % 4) reads 32 contiguous bytes of pixel r (and of pixel r + 8) per 64-channel
+//     block - the 4 lanes of a pixel cover one full 128-byte line - and serves 4 k-steps from them: in k-step s of block
+//     ss, k-slots {2j, 2j+1} are channels 64 ss + 16 j + 4 s + {0, 1} and k-slots {2j+8, 2j+9} are ... + {2, 3}.
+//   * B fragments (the weights in the operand format, same permutation, n >= 3 zero) are laid out once per weight upload
+//     as wf[(tap * C/64 + ss) * 4 + s][lane] = {b0, b1} (out_conv_pack_kernel) and staged in shared memory per block.
+//   * block = 8 warps = 8 consecutive rows x 16 pixels, so the 3 input rows of a warp are shared through L1 with its
+//     neighbours; zero padding = predicated loads.
+// The fp32 exact mode keeps the CUDA-core kernel (fp32 weights and activations).
+// -------------------------------------------------------------------------------------
+template <typename H>
+__global__ void out_conv_pack_kernel(const float* __restrict__ w /*[3][C][3][3]*/, uint2* __restrict__ wf, int C) {
+  const int CB = C / 64;
+  const int total = 9 * CB * 4 * 32;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int lane = idx & 31, ks = idx >> 5;
+  const int s = ks & 3, ss = (ks >> 2) % CB, t = ks / (4 * CB);
+  const int j = lane & 3, n = lane >> 2;
+  const int c0 = 64 * ss + 16 * j + 4 * s;
+  uint2 v = make_uint2(0u, 0u);
+  if (n < 3) {
+    const float* wn = w + (int64_t)n * C * 9 + t;
+    v.x = pack_h2<H>(__ldg(wn + (int64_t)(c0 + 0) * 9), __ldg(wn + (int64_t)(c0 + 1) * 9));
+    v.y = pack_h2<H>(__ldg(wn + (int64_t)(c0 + 2) * 9), __ldg(wn + (int64_t)(c0 + 3) * 9));
+  }
+  wf[idx] = v;
+}
+
+template <typename H>
+__device__ __forceinline__ void mma_m16n8k16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                             uint32_t b1) {
+  if constexpr (H16<H>::UMMA_FMT == 1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  } else {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
+}
+
+constexpr int OM_ROWS = 8, OM_PIX = 16;   // block tile: 8 rows x 16 pixels, one warp per row
+template <typename H>
+__global__ void __launch_bounds__(32 * OM_ROWS)
+out_conv_mma_kernel(const H* __restrict__ a, const uint2* __restrict__ wf, const float* __restrict__ bias,
+                    float* __restrict__ out_f32, uint8_t* __restrict__ out_u8, int Hh, int W, int C) {
+  extern __shared__ __align__(16) uint2 om_wf[];               // [9 * C/16][32]
+  const int CB = C / 64;
+  const int nfrag = 9 * CB * 4 * 32;
+  for (int i = threadIdx.x; i < nfrag / 2; i += blockDim.x)
+    reinterpret_cast<uint4*>(om_wf)[i] = __ldg(reinterpret_cast<const uint4*>(wf) + i);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.z, y = blockIdx.y * OM_ROWS + warp, x0 = blockIdx.x * OM_PIX;
+  if (y >= Hh) return;
+  const int r = lane >> 2, j = lane & 3;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int t = 0; t < 9; ++t) {
+    const int yy = y + t / 3 - 1;
+    const int xa = x0 + r + t % 3 - 1, xb = xa + 8;
+    const bool rowok = yy >= 0 && yy < Hh;
+    const bool va = rowok && xa >= 0 && xa < W, vb = rowok && xb >= 0 && xb < W;
+    const H* pa = a + (((int64_t)n * Hh + yy) * W + xa) * C + 16 * j;
+    const H* pb = pa + (int64_t)8 * C;
+    for (int ss = 0; ss < CB; ++ss) {
+      uint4 qa0 = make_uint4(0, 0, 0, 0), qa1 = qa0, qb0 = qa0, qb1 = qa0;
+      if (va) {
+        qa0 = __ldg(reinterpret_cast<const uint4*>(pa + 64 * ss));
+        qa1 = __ldg(reinterpret_cast<const uint4*>(pa + 64 * ss + 8));
+      }
+      if (vb) {
+        qb0 = __ldg(reinterpret_cast<const uint4*>(pb + 64 * ss));
+        qb1 = __ldg(reinterpret_cast<const uint4*>(pb + 64 * ss + 8));
+      }
+      const uint2* bf = om_wf + ((t * CB + ss) * 4) * 32 + lane;
+      const uint2 b0 = bf[0], b1 = bf[32], b2 = bf[64], b3 = bf[96];
+      mma_m16n8k16<H>(acc, qa0.x, qb0.x, qa0.y, qb0.y, b0.x, b0.y);   // s = 0: channels +0..3
+      mma_m16n8k16<H>(acc, qa0.z, qb0.z, qa0.w, qb0.w, b1.x, b1.y);   // s = 1: +4..7
+      mma_m16n8k16<H>(acc, qa1.x, qb1.x, qa1.y, qb1.y, b2.x, b2.y);   // s = 2: +8..11
+      mma_m16n8k16<H>(acc, qa1.z, qb1.z, qa1.w, qb1.w, b3.x, b3.y);   // s = 3: +12..15
+    }
+  }
+  // accumulator layout: acc[0], acc[1] = pixel r, outputs 2j, 2j+1; acc[2], acc[3] = pixel r + 8
+  auto put = [&](int co, int x, float v) {
+    if (x >= W) return;
+    v += __ldg(bias + co);
+    const int64_t o = (((int64_t)n * 3 + co) * Hh + y) * W + x;
+    if (out_f32) out_f32[o] = v;
+    if (out_u8) out_u8[o] = (uint8_t)fminf(fmaxf((v + 1.f) * 127.5f, 0.f), 255.f);
+  };
+  if (j == 0) {
+    put(0, x0 + r, acc[0]); put(1, x0 + r, acc[1]);
+    put(0, x0 + r + 8, acc[2]); put(1, x0 + r + 8, acc[3]);
+  } else if (j == 1) {
+    put(2, x0 + r, acc[0]);
+    put(2, x0 + r + 8, acc[2]);
+  }
+}
+
+int launch_out_conv_pack(const float* w, void* wf, int o16, int C, cudaStream_t st) {
+  GN_REQUIRE(o16 != 0 && C % 64 == 0, "output conv (tensor path): 16-bit operands and C %% 64 == 0");
+  const int total = 9 * (C / 64) * 4 * 32;
+  if (o16 == 2) out_conv_pack_kernel<f16><<<ceil_div(total, 256), 256, 0, st>>>(w, static_cast<uint2*>(wf), C);
+  else out_conv_pack_kernel<bf16><<<ceil_div(total, 256), 256, 0, st>>>(w, static_cast<uint2*>(wf), C);
+  GN_CUDA_CHECK(cudaGetLastError());
+  return GN_OK;
+}
+
+int launch_out_conv_mma(const void* a, int o16, const void* wf, const float* bias, float* out_f32, uint8_t* out_u8, int B,
+                        int H, int W, int C, cudaStream_t st) {
+  GN_REQUIRE(o16 != 0 && C % 64 == 0 && C <= 512, "output conv (tensor path): 16-bit operands, C %% 64 == 0, C <= 512");
+  const size_t smem = (size_t)9 * (C / 16) * 32 * sizeof(uint2);      // 18 KB for C = 128
+  GN_REQUIRE(B <= 65535, "output conv: too many images per pass");
+  dim3 grid(ceil_div(W, OM_PIX), ceil_div(H, OM_ROWS), B);
+  if (o16 == 2) {
+    static DevSmemOptIn optin;
+    GN_CUDA_CHECK(ensure_smem_optin(optin, out_conv_mma_kernel<f16>, (int)smem));
+    out_conv_mma_kernel<f16><<<grid, 32 * OM_ROWS, smem, st>>>(static_cast<const f16*>(a), static_cast<const uint2*>(wf), bias,
+                                                              out_f32, out_u8, H, W, C);
+  } else {
+    static DevSmemOptIn optin;
+    GN_CUDA_CHECK(ensure_smem_optin(optin, out_conv_mma_kernel<bf16>, (int)smem));
+    out_conv_mma_kernel<bf16><<<grid, 32 * OM_ROWS, smem, st>>>(static_cast<const bf16*>(a), static_cast<const uint2*>(wf),
+                                                               bias, out_f32, out_u8, H, W, C);
+  }
+  GN_CUDA_CHECK(cudaGetLastError());
+  ++g_launch_count;
+  return GN_OK;
+}
+
 // conv weight repack: PyTorch [Cout, Cin, kh, kw] fp32 -> [Cout, kh*kw, Cin] bf16 (tap-major K for the implicit GEMM)
 template <typename OutT>
 __global__ void repack_conv_w_kernel(const float* __restrict__ w, OutT* __restrict__ out, int Cout, int Cin, int taps) {

@@ -14,5 +14,10 @@ int launch_vq_tail(const int32_t* ids, const float* w, const float* bias, float*
                    int little_endian, cudaStream_t st);
 int launch_out_conv(const void* a, int o16, const float* w, const float* bias, float* out_f32, uint8_t* out_u8, int B, int H,
                     int W, int C, cudaStream_t st);
+// tensor-core output conv (16-bit operand modes): `wf` = fragment-ordered weights, 9 * C/16 * 32 uint2, built by
+// launch_out_conv_pack whenever decoder.conv_out.weight changes
+int launch_out_conv_pack(const float* w, void* wf, int o16, int C, cudaStream_t st);
+int launch_out_conv_mma(const void* a, int o16, const void* wf, const float* bias, float* out_f32, uint8_t* out_u8, int B,
+                        int H, int W, int C, cudaStream_t st);
 int launch_repack_conv_w(const float* w, void* out, int o16, int Cout, int Cin, int taps, cudaStream_t st);
 }  // namespace gn

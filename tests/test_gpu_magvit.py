@@ -102,13 +102,21 @@ def test_decode_matches_reference(setup):
     assert rel_fro(m.decode(q.cuda()), rec) < 1e-6                    # VQModel.decode(quant) seam
 
 
-def test_roundtrip_and_batching(setup):
+def test_roundtrip_and_batching(setup, monkeypatch):
     pkg, z, cfg, sd, m = setup
     g = torch.Generator().manual_seed(123)
-    img = torch.rand(11, 3, 256, 256, generator=g) * 2 - 1           # crosses the 8-image workspace chunk
+    img = torch.rand(11, 3, 256, 256, generator=g) * 2 - 1
     ids = m.encode_to_tokens(img.cuda())
     one = torch.cat([m.encode_to_tokens(img[i:i + 1].cuda()) for i in range(11)])
     assert torch.equal(ids, one)                                       # per-image results independent of batching
+    # ... and of the number of images per pass through the trunk (default 32): 4 per pass = 3 passes, the last one ragged
+    monkeypatch.setenv("GENIE_B200_VQ_PER", "4")
+    m4 = pkg.VQModel(precision="bf16")
+    m4.load_state_dict(sd, strict=True)
+    m4 = m4.to("cuda")
+    assert torch.equal(m4.encode_to_tokens(img.cuda()), ids)
+    assert torch.equal(m4.decode_tokens(ids, as_uint8=True), m.decode_tokens(ids, as_uint8=True))
+    monkeypatch.delenv("GENIE_B200_VQ_PER")
     dec = pkg.decode_latents_wrapper(m, batch_size=4)
     frames = dec(ids.cpu().numpy())
     assert frames.shape == (11, 3, 256, 256) and frames.dtype == torch.uint8
