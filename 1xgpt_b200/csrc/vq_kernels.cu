@@ -101,7 +101,8 @@ int launch_stem_conv(const float* img, const float* w, float* out, int B, int H,
   GN_REQUIRE((size_t)9 * (W + 2) * sizeof(float) <= 48 * 1024, "stem conv: image width %d too large", W);
   // 8 rows per block when the 10 staged rows fit the default 48 KB of shared memory (W <= 407), else one row per block.
   // GENIE_B200_STEM_ROWS=1 forces the one-row variant (A/B; results are bit-identical)
-  static const bool one_row = [] { const char* e = getenv("GENIE_B200_STEM_ROWS"); return e && e[0] == '1'; }();
+  const char* sr = getenv("GENIE_B200_STEM_ROWS");   // once per encode pass: re-read so that tests can flip it
+  const bool one_row = sr && sr[0] == '1';
   if (!one_row && (size_t)3 * 10 * (W + 2) * sizeof(float) <= 48 * 1024)
     return launch_stem_rows<8>(img, w, out, B, H, W, Cout, st);
   return launch_stem_rows<1>(img, w, out, B, H, W, Cout, st);
@@ -252,6 +253,193 @@ int launch_gn_swish(const float* x, double* stats, const float* gamma, const flo
   GN_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;
   return GN_OK;
+}
+
+// -------------------------------------------------------------------------------------
+// GroupNorm statistics + apply + swish in ONE persistent kernel (16-bit operand modes).
+// The two-kernel form above reads the fp32 trunk twice from HBM (statistics pass, apply pass) and writes the operand:
+// 10 bytes per element, 30 % of an encode + decode pass.  Here a chunk of an image is summed (phase 1) and normalised
+// (phase 2) by the SAME block a short time apart, so the second read is served by L2: 6 bytes per element of HBM traffic.
+//   * work item = (image n, chunk c) of `ppb` pixels (64 KB of fp32); block b takes items b, b + grid, ... in order
+//   * phase 1(item): the block's partial {sum, sumsq} per group -> partial[n][c][g]; the block whose ticket completes
+//     image n folds the image's partials IN CHUNK-INDEX ORDER (deterministic, as above) into {mean, rstd}, then
+//     publishes ready[n] = epoch (release)
+//   * phase 2(item) = the apply pass on the item's pixels, after an acquire spin on ready[n].  A block runs
+//     phase 1(item k) BEFORE phase 2(item k - 1): the fold of an image overlaps the next item's loads, and the in-flight
+//     footprint is 2 items per block (2 x 592 x 64 KB = 76 MB < L2).
+//   * progress: every block reaches phase 1 of its item of image n without waiting on image n itself (only on earlier
+//     images), so by induction over n every image completes - provided all blocks are co-resident: the grid is sized by
+//     the occupancy calculator and launched with cudaLaunchCooperativeKernel, which enforces exactly that.
+// The per-element arithmetic equals gn_apply_swish_kernel's; the statistics differ from the two-kernel form only by the
+// chunking of the fixed-order sum, which is why the fp32 exact mode (token ids equal to the reference's) keeps that form.
+// -------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+gn_fused_kernel(const float* __restrict__ x, double* __restrict__ partial, double* __restrict__ stats,
+                unsigned int* __restrict__ tickets, unsigned int* __restrict__ ready, unsigned int epoch,
+                const float* __restrict__ gamma, const float* __restrict__ beta, OutT* __restrict__ out, int HW, int C,
+                int ppb, int chunks, int n_items) {
+  __shared__ float s_sum[256], s_sq[256];
+  __shared__ bool s_last;
+  const int cg = C / 32;                 // channels per group (4, 8, 16, 32)
+  const int vpp = C / 4;                 // float4 per pixel; 256 % vpp == 0 -> each thread owns one channel quad
+  const int tid = threadIdx.x;
+  const int v = tid % vpp, g_of_thread = (v * 4) / cg;
+  const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + v);
+  const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + v);
+
+  auto phase1 = [&](int item) {
+    const int n = item / chunks, c = item % chunks;
+    const int p0 = c * ppb, p1 = min(p0 + ppb, HW);
+    const float4* base = reinterpret_cast<const float4*>(x + (int64_t)n * HW * C) + (int64_t)p0 * vpp;
+    const int total = (p1 - p0) * vpp;
+    float sum = 0.f, sq = 0.f;
+    for (int i = tid; i < total; i += 256) {
+      const float4 f = base[i];
+      sum += (f.x + f.y) + (f.z + f.w);
+      sq += (f.x * f.x + f.y * f.y) + (f.z * f.z + f.w * f.w);
+    }
+    __syncthreads();                     // s_sum / s_sq / s_last of the previous item are no longer read
+    s_sum[tid] = sum;
+    s_sq[tid] = sq;
+    __syncthreads();
+    if (tid < 32) {
+      const int g = tid;
+      const int q0 = g * cg / 4, q1 = (g + 1) * cg / 4;   // channel quads of this group
+      double a = 0.0, b2 = 0.0;
+      for (int t0 = 0; t0 < 256; t0 += vpp)
+        for (int q = q0; q < q1; ++q) { a += (double)s_sum[t0 + q]; b2 += (double)s_sq[t0 + q]; }
+      double* o = partial + (((int64_t)n * chunks + c) * 32 + g) * 2;
+      o[0] = a;
+      o[1] = b2;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int t = atomicAdd(&tickets[n], 1u);
+      s_last = (t == (unsigned int)chunks - 1);
+      if (s_last) tickets[n] = 0;        // ready for the next launch on this stream
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int g = tid >> 3, j = tid & 7;
+    double a = 0.0, b = 0.0;
+#pragma unroll 8
+    for (int cc = j; cc < chunks; cc += 8) {
+      const double2 p = __ldcg(reinterpret_cast<const double2*>(partial + (((int64_t)n * chunks + cc) * 32 + g) * 2));
+      a += p.x;
+      b += p.y;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      a += __shfl_down_sync(0xffffffffu, a, o, 8);
+      b += __shfl_down_sync(0xffffffffu, b, o, 8);
+    }
+    if (j == 0) {
+      const double cnt = (double)HW * (C / 32);
+      const double mean = a / cnt;
+      const double var = fmax(b / cnt - mean * mean, 0.0);
+      reinterpret_cast<float2*>(stats)[(int64_t)n * 32 + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-6)));
+    }
+    __syncthreads();                     // the 32 statistics are written ...
+    if (tid == 0) {
+      __threadfence();                   // ... and visible device-wide before the flag
+      st_release_u32(&ready[n], epoch);
+    }
+  };
+
+  auto phase2 = [&](int item) {
+    const int n = item / chunks, c = item % chunks;
+    if (tid == 0) {
+      while (ld_acquire_u32(&ready[n]) != epoch) __nanosleep(64);
+    }
+    __syncthreads();
+    const float2 ms = __ldcg(reinterpret_cast<const float2*>(stats) + (int64_t)n * 32 + g_of_thread);
+    const float mean = ms.x, rstd = ms.y;
+    const int p0 = c * ppb, p1 = min(p0 + ppb, HW);
+    const int64_t off = ((int64_t)n * HW + p0) * vpp;            // in float4 / 4-element vectors
+    const float4* base = reinterpret_cast<const float4*>(x) + off;
+    const int total = (p1 - p0) * vpp;
+    for (int i = tid; i < total; i += 256) {
+      const float4 f = __ldcs(base + i);
+      float y[4] = {(f.x - mean) * rstd * gm.x + bt.x, (f.y - mean) * rstd * gm.y + bt.y, (f.z - mean) * rstd * gm.z + bt.z,
+                    (f.w - mean) * rstd * gm.w + bt.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) y[k] = y[k] / (1.f + __expf(-y[k]));
+      uint2 p;
+      p.x = pack_h2<OutT>(y[0], y[1]);
+      p.y = pack_h2<OutT>(y[2], y[3]);
+      reinterpret_cast<uint2*>(out)[off + i] = p;
+    }
+  };
+
+  int prev = -1;
+  for (int item = blockIdx.x;; item += gridDim.x) {
+    if (item < n_items) phase1(item);
+    if (prev >= 0) phase2(prev);
+    if (item >= n_items) break;
+    prev = item;
+  }
+}
+
+constexpr int kGnFusedMaxChunks = 512;
+// -> GN_OK and *done = true when the fused kernel ran; *done = false when this shape is left to the two-kernel form
+template <typename OutT>
+static int launch_gn_fused_t(const float* x, double* stats, unsigned int* ready, unsigned int epoch, const float* gamma,
+                             const float* beta, OutT* out, int B, int HW, int C, cudaStream_t st, bool* done) {
+  *done = false;
+  if (!(C % 128 == 0 && 1024 % C == 0) || B > 128) return GN_OK;
+  int ppb = 65536 / (C * 4);             // 64 KB of fp32 per item
+  if (ppb < 8) ppb = 8;
+  while (ceil_div(HW, ppb) > kGnFusedMaxChunks) ppb *= 2;
+  const int chunks = ceil_div(HW, ppb);
+  const int n_items = B * chunks;
+  static int blocks_per_sm_dev[kMaxDevices] = {};
+  int& bps = blocks_per_sm_dev[current_device()];
+  if (!bps) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gn_fused_kernel<OutT>, 256, 0) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      return GN_OK;
+    }
+    bps = n < 4 ? n : 4;                 // 4 x 148 blocks x 2 items x 64 KB = 76 MB in flight: inside L2
+  }
+  int grid = bps * device_sm_count();
+  if (grid > n_items) grid = n_items;
+  // the progress argument needs at most two items of one block inside one image: chunks <= 2 * grid (B200: grid = 592
+  // or one item per block); anything else takes the two-kernel form
+  if (chunks > 2 * grid) return GN_OK;
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(stats);
+  double* fin = stats + kStatsOff;
+  double* partial = stats + kStatsOff + (int64_t)B * 64;
+  int ppb_ = ppb, chunks_ = chunks, items_ = n_items, HW_ = HW, C_ = C;
+  void* args[] = {(void*)&x, (void*)&partial, (void*)&fin, (void*)&tickets, (void*)&ready, (void*)&epoch, (void*)&gamma,
+                  (void*)&beta, (void*)&out, (void*)&HW_, (void*)&C_, (void*)&ppb_, (void*)&chunks_, (void*)&items_};
+  GN_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)gn_fused_kernel<OutT>, dim3(grid), dim3(256), args, 0, st));
+  ++g_launch_count;
+  *done = true;
+  return GN_OK;
+}
+
+int launch_gn_swish_fused(const float* x, double* stats, unsigned int* ready, unsigned int epoch, const float* gamma,
+                          const float* beta, void* out, int o16, int B, int HW, int C, cudaStream_t st) {
+  bool done = false;
+  if (o16 == 2)
+    GN_PROPAGATE(launch_gn_fused_t<f16>(x, stats, ready, epoch, gamma, beta, static_cast<f16*>(out), B, HW, C, st, &done));
+  else if (o16 == 1)
+    GN_PROPAGATE(launch_gn_fused_t<bf16>(x, stats, ready, epoch, gamma, beta, static_cast<bf16*>(out), B, HW, C, st, &done));
+  if (done) return GN_OK;
+  return launch_gn_swish(x, stats, gamma, beta, out, o16, B, HW, C, st);
 }
 
 // -------------------------------------------------------------------------------------

@@ -59,6 +59,9 @@ struct gn_vq {
   int o16 = 2;           // operand format: 2 = fp16 (default), 1 = bf16, 0 = fp32 on the CUDA-core kernels (exact mode)
   void* dec_out_frag = nullptr;   // decoder.conv_out weights in mma fragment order (16-bit modes, launch_out_conv_pack)
   bool out_frag_dirty = true;
+  unsigned int* gn_ready = nullptr;   // per-image "statistics ready" flags of the fused GroupNorm kernel
+  unsigned int gn_epoch = 0;          // launch counter: the flag value of the current launch
+  bool gn_fused = false;              // GENIE_B200_GN_FUSED: one persistent GroupNorm kernel (16-bit modes)
   bool out_conv_mma = true;       // GENIE_B200_OUT_CONV_MMA=0: output conv on the CUDA-core kernel (A/B)
   int per = 32;          // images per pass through the trunk (GENIE_B200_VQ_PER; workspace = per x ~120 MB at 256x256)
   size_t esz() const { return o16 ? 2 : 4; }
@@ -96,9 +99,14 @@ int ensure_ws(gn_vq* m, int imgs, int H, int W) {
   GN_PROPAGATE(valloc(m, (void**)&m->r, elems * 4));
   GN_PROPAGATE(valloc(m, (void**)&m->a, elems * m->esz()));
   // final stats + last-block tickets (zeroed once; every launch leaves them at zero) + partials
-  const size_t stat_bytes = (64 + (size_t)imgs * (64 + 64 * 64)) * sizeof(double);
+  // (partials: up to 512 chunks x 32 groups x {sum, sumsq} per image for the fused kernel, 64 chunks for the two-kernel form)
+  const size_t stat_bytes = (64 + (size_t)imgs * (64 + 512 * 64)) * sizeof(double);
   GN_PROPAGATE(valloc(m, (void**)&m->stats, stat_bytes));
   GN_CUDA_CHECK(cudaMemset(m->stats, 0, stat_bytes));
+  if (!m->gn_ready) {
+    GN_PROPAGATE(valloc(m, (void**)&m->gn_ready, 128 * sizeof(unsigned int)));
+    GN_CUDA_CHECK(cudaMemset(m->gn_ready, 0, 128 * sizeof(unsigned int)));
+  }
   m->cap_imgs = imgs; m->cap_H = H; m->cap_W = W;
   return GN_OK;
 }
@@ -118,10 +126,18 @@ int conv(gn_vq* m, const ConvW& w, const void* a, int B, int Hi, int Wi, int str
   return linear_forward(la, st);
 }
 
+// swish(GroupNorm(x)) -> m->a in the operand format: one persistent kernel in the 16-bit modes (GENIE_B200_GN_FUSED),
+// statistics pass + apply pass otherwise
+int gn_swish(gn_vq* m, const float* x, const NormW& nw, int B, int HW, int C, cudaStream_t st) {
+  if (m->gn_fused && m->o16 != 0)
+    return launch_gn_swish_fused(x, m->stats, m->gn_ready, ++m->gn_epoch, nw.g, nw.b, m->a, m->o16, B, HW, C, st);
+  return launch_gn_swish(x, m->stats, nw.g, nw.b, m->a, m->o16, B, HW, C, st);
+}
+
 // ResBlock (improved_model.py:36-51): x -> x + / nin(x) + conv2(swish(GN(conv1(swish(GN(x))))));  result in m->x
 int resblock(gn_vq* m, const ResW& rw, int B, int H, int W, cudaStream_t st) {
   const int HW = H * W;
-  GN_PROPAGATE(launch_gn_swish(m->x, m->stats, rw.n1.g, rw.n1.b, m->a, m->o16, B, HW, rw.cin, st));
+  GN_PROPAGATE(gn_swish(m, m->x, rw.n1, B, HW, rw.cin, st));
   GN_PROPAGATE(conv(m, rw.c1, m->a, B, H, W, 1, nullptr, m->y, st));
   const float* resid = m->x;
   if (rw.cin != rw.cout) {
@@ -130,7 +146,7 @@ int resblock(gn_vq* m, const ResW& rw, int B, int H, int W, cudaStream_t st) {
     GN_PROPAGATE(conv(m, rw.nin, m->a, B, H, W, 1, nullptr, m->r, st));
     resid = m->r;
   }
-  GN_PROPAGATE(launch_gn_swish(m->y, m->stats, rw.n2.g, rw.n2.b, m->a, m->o16, B, HW, rw.cout, st));
+  GN_PROPAGATE(gn_swish(m, m->y, rw.n2, B, HW, rw.cout, st));
   GN_PROPAGATE(conv(m, rw.c2, m->a, B, H, W, 1, resid, rw.cin != rw.cout ? m->x : m->x, st));
   return GN_OK;
 }
@@ -214,6 +230,8 @@ int gn_vq_create(gn_vq** out, const gn_vq_config* cfg, int device) {
     const char* e = getenv("GENIE_B200_VQ_PER");
     const int v = e ? atoi(e) : 0;
     if (v >= 1 && v <= 64) m->per = v;
+    const char* gf = getenv("GENIE_B200_GN_FUSED");
+    m->gn_fused = gf ? (gf[0] != '0') : false;
     const char* oc = getenv("GENIE_B200_OUT_CONV_MMA");
     m->out_conv_mma = oc ? (oc[0] != '0') : true;   // measured: 1549 -> 436 us per 32 images, decode 2335 -> 2500 img/s
   }
@@ -367,7 +385,7 @@ int gn_vq_decode(gn_vq* m, const int32_t* ids, int B, int h0, int w0, int little
         h *= 2; w *= 2;
       }
     }
-    GN_PROPAGATE(launch_gn_swish(m->x, m->stats, m->dec_norm.g, m->dec_norm.b, m->a, m->o16, n, h * w, m->ch[0], st));
+    GN_PROPAGATE(gn_swish(m, m->x, m->dec_norm, n, h * w, m->ch[0], st));
     float* of = img_f32 ? img_f32 + (int64_t)b0 * 3 * H * W : nullptr;
     uint8_t* ou = img_u8 ? img_u8 + (int64_t)b0 * 3 * H * W : nullptr;
     if (m->out_conv_mma && m->o16 != 0 && m->ch[0] % 64 == 0 && w % 16 == 0) {
