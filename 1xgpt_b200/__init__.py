@@ -16,7 +16,7 @@ from .model import (  # noqa: E402
     FactorizedEmbedding, ModelOutput, cosine_schedule,
 )
 from .vq import VQModel, VQConfig, decode_latents_wrapper  # noqa: E402
-from .synth import synthetic_state_dict  # noqa: E402
+from .synth import synthetic_state_dict, synthetic_vq_state_dict  # noqa: E402
 from .eval_utils import AvgMetric, compute_loss, decode_tokens  # noqa: E402
 from .evaluate import GenieEvaluator  # noqa: E402
 from .data import RawTokenDataset, get_maskgit_collator  # noqa: E402
@@ -26,6 +26,6 @@ __all__ = [
     "GenieConfig", "STMaskGIT", "STTransformerDecoder", "STBlock", "Mlp", "SelfAttention", "BasicSelfAttention",
     "MemoryEfficientAttention", "FactorizedEmbedding", "ModelOutput", "cosine_schedule", "factorize_token_ids",
     "unfactorize_token_ids", "factorize_labels", "nth_root", "GnError", "VQModel", "VQConfig", "decode_latents_wrapper",
-    "synthetic_state_dict", "AvgMetric", "compute_loss", "decode_tokens", "GenieEvaluator", "RawTokenDataset",
+    "synthetic_state_dict", "synthetic_vq_state_dict", "AvgMetric", "compute_loss", "decode_tokens", "GenieEvaluator", "RawTokenDataset",
     "get_maskgit_collator",
 ]

@@ -53,3 +53,18 @@ def synthetic_state_dict(cfg: GenieConfig, seed: int = 0, std: float = 0.02, bia
     sd["out_x_proj.weight"] = n(V, d) * readout_gain
     sd["out_x_proj.bias"] = b(V)
     return sd
+
+
+def synthetic_vq_state_dict(template: Dict[str, torch.Tensor], seed: int = 31) -> Dict[str, torch.Tensor]:
+    """Seeded synthetic MAGVIT2 weights for throughput runs (no checkpoint reachable): fan-in scaled convolutions,
+    GroupNorm affine near identity, small biases.  `template` = state_dict() of a VQModel (keys and shapes)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, v in template.items():
+        if v.dim() == 4:
+            sd[k] = torch.randn(v.shape, generator=g) / (v.shape[1] * v.shape[2] * v.shape[3]) ** 0.5
+        elif "norm" in k and k.endswith(".weight"):
+            sd[k] = 1.0 + 0.1 * torch.randn(v.shape, generator=g)
+        else:
+            sd[k] = 0.05 * torch.randn(v.shape, generator=g)
+    return sd

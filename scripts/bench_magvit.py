@@ -20,15 +20,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
 m = pkg.VQModel(precision=os.environ.get("GENIE_PRECISION", "fp16"))
 # seeded synthetic weights (no checkpoint reachable): fan-in scaled convs, GroupNorm affine near identity
-_g = torch.Generator().manual_seed(31)
-_sd = {}
-for _k, _v in m.state_dict().items():
-    if _v.dim() == 4:
-        _sd[_k] = torch.randn(_v.shape, generator=_g) / (_v.shape[1] * _v.shape[2] * _v.shape[3]) ** 0.5
-    elif "norm" in _k and _k.endswith(".weight"):
-        _sd[_k] = 1.0 + 0.1 * torch.randn(_v.shape, generator=_g)
-    else:
-        _sd[_k] = 0.05 * torch.randn(_v.shape, generator=_g)
+_sd = pkg.synthetic_vq_state_dict(m.state_dict(), seed=31)
 m.load_state_dict(_sd)
 m = m.to("cuda")
 img = (torch.rand(B, 3, 256, 256, generator=torch.Generator().manual_seed(7 + rank)) * 2 - 1).cuda()

@@ -14,15 +14,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 pkg = importlib.import_module("1xgpt_b200")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 m = pkg.VQModel(precision=os.environ.get("GENIE_PRECISION", "fp16"))
-g = torch.Generator().manual_seed(31)
-sd = {}
-for k, v in m.state_dict().items():
-    if v.dim() == 4:
-        sd[k] = torch.randn(v.shape, generator=g) / (v.shape[1] * v.shape[2] * v.shape[3]) ** 0.5
-    elif "norm" in k and k.endswith(".weight"):
-        sd[k] = 1.0 + 0.1 * torch.randn(v.shape, generator=g)
-    else:
-        sd[k] = 0.05 * torch.randn(v.shape, generator=g)
+sd = pkg.synthetic_vq_state_dict(m.state_dict(), seed=31)
 m.load_state_dict(sd)
 m = m.to("cuda")
 img = (torch.rand(B, 3, 256, 256, generator=torch.Generator().manual_seed(7)) * 2 - 1).cuda()
