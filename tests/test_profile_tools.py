@@ -59,3 +59,21 @@ def test_round2_ncu_evidence_reproducible(tmp_path):
                     str(tmp_path / "t.json"), "test"], check=True, capture_output=True)
     t_new, t_ref = json.load(open(tmp_path / "t.json")), json.load(open(os.path.join(PROF, "r02_gemm_insitu_traffic.json")))
     assert abs(t_new["avg_dram_bytes_per_gemm_launch"] - t_ref["avg_dram_bytes_per_gemm_launch"]) < 1.0
+
+
+def test_round2b_magvit_launch_lists_reproducible(tmp_path):
+    """second round-2 session: the three MAGVIT2 launch-share tables (32 images per pass; + CTA-pair conv tiles and the
+    mma.sync output conv; + the fused GroupNorm kernel) are regenerated from the committed raw ncu launch lists."""
+    for raw, md in (("r02b_vq_launches_per32", "r02b_launch_shares_magvit_per32"),
+                    ("r02b_vq_launches_pair_mma", "r02b_launch_shares_magvit_pair_mma"),
+                    ("r02b_vq_launches_gn_fused", "r02b_launch_shares_magvit_gn_fused")):
+        csv_path = tmp_path / (raw + ".csv")
+        with gzip.open(os.path.join(PROF, "r02b_ncu", raw + ".csv.gz"), "rt") as f:
+            csv_path.write_text(f.read())
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "summarize_launches.py"), str(csv_path), "t"],
+                           check=True, capture_output=True, text=True)
+        committed = open(os.path.join(PROF, md + ".md")).read()
+        rows = [ln for ln in r.stdout.splitlines() if ln.startswith("| `")]
+        assert len(rows) >= 12
+        for ln in rows:
+            assert ln in committed, (md, ln)
