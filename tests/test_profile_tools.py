@@ -77,3 +77,17 @@ def test_round2b_magvit_launch_lists_reproducible(tmp_path):
         assert len(rows) >= 12
         for ln in rows:
             assert ln in committed, (md, ln)
+
+
+def test_round2b_ncu_pages_reproducible(tmp_path):
+    """--set full pages of the two MAGVIT2 kernels that replaced round-2 ones (8-row stem conv, mma.sync output conv)."""
+    raw = os.path.join(PROF, "r02b_ncu", "r02b_vq_new_raw.csv.gz")
+    subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), str(tmp_path / "k"), raw], check=True,
+                   capture_output=True)
+    new = json.load(open(tmp_path / "k.json"))
+    ref = json.load(open(os.path.join(PROF, "r02b_ncu_kernels.json")))
+    assert [k["kernel"] for k in new["kernels"]] == [k["kernel"] for k in ref["kernels"]]
+    names = " ".join(k["kernel"] for k in new["kernels"])
+    assert "stem_conv_kernel<4, 8>" in names and "out_conv_mma_kernel" in names
+    for k in new["kernels"]:
+        assert k["avg_us"] > 0 and k["hbm_gbs"] > 0
