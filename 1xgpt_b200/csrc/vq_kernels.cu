@@ -740,8 +740,19 @@ __device__ __forceinline__ void mma_m16n8k16(float (&c)[4], uint32_t a0, uint32_
   }
 }
 
+// 32 contiguous bytes through the non-coherent path as ONE 256-bit load (LDG.E.256, sm_100): the 4 lanes of a pixel then
+// cover its full 128-byte line with one instruction.  Motivation: with two 128-bit loads ncu shows l1tex throughput at
+// 95 % (a warp-wide 128-bit load of this fragment layout touches 8 lines for 512 bytes).  MEASURED AND LEFT OFF
+// (GENIE_B200_OUT_CONV_L256=1; frames bit-identical): decode 2441 / 2400 img/s vs 2517 / 2456 with 128-bit loads, same
+// process, interleaved (scripts/out_conv_l256_check.py, profiles/r02b_out_conv_l256_ab.json).
+__device__ __forceinline__ void ldg256(const void* p, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+               : "l"(p));
+}
+
 constexpr int OM_ROWS = 8, OM_PIX = 16;   // block tile: 8 rows x 16 pixels, one warp per row
-template <typename H>
+template <typename H, bool L256>
 __global__ void __launch_bounds__(32 * OM_ROWS)
 out_conv_mma_kernel(const H* __restrict__ a, const uint2* __restrict__ wf, const float* __restrict__ bias,
                     float* __restrict__ out_f32, uint8_t* __restrict__ out_u8, int Hh, int W, int C) {
@@ -766,13 +777,18 @@ out_conv_mma_kernel(const H* __restrict__ a, const uint2* __restrict__ wf, const
     const H* pb = pa + (int64_t)8 * C;
     for (int ss = 0; ss < CB; ++ss) {
       uint4 qa0 = make_uint4(0, 0, 0, 0), qa1 = qa0, qb0 = qa0, qb1 = qa0;
-      if (va) {
-        qa0 = __ldg(reinterpret_cast<const uint4*>(pa + 64 * ss));
-        qa1 = __ldg(reinterpret_cast<const uint4*>(pa + 64 * ss + 8));
-      }
-      if (vb) {
-        qb0 = __ldg(reinterpret_cast<const uint4*>(pb + 64 * ss));
-        qb1 = __ldg(reinterpret_cast<const uint4*>(pb + 64 * ss + 8));
+      if constexpr (L256) {
+        if (va) ldg256(pa + 64 * ss, qa0, qa1);
+        if (vb) ldg256(pb + 64 * ss, qb0, qb1);
+      } else {
+        if (va) {
+          qa0 = __ldg(reinterpret_cast<const uint4*>(pa + 64 * ss));
+          qa1 = __ldg(reinterpret_cast<const uint4*>(pa + 64 * ss + 8));
+        }
+        if (vb) {
+          qb0 = __ldg(reinterpret_cast<const uint4*>(pb + 64 * ss));
+          qb1 = __ldg(reinterpret_cast<const uint4*>(pb + 64 * ss + 8));
+        }
       }
       const uint2* bf = om_wf + ((t * CB + ss) * 4) * 32 + lane;
       const uint2 b0 = bf[0], b1 = bf[32], b2 = bf[64], b3 = bf[96];
@@ -808,22 +824,31 @@ int launch_out_conv_pack(const float* w, void* wf, int o16, int C, cudaStream_t 
   return GN_OK;
 }
 
+template <typename H, bool L256>
+static int launch_om(const void* a, const void* wf, const float* bias, float* out_f32, uint8_t* out_u8, dim3 grid, size_t smem,
+                     int Hh, int W, int C, cudaStream_t st) {
+  static DevSmemOptIn optin;             // one per kernel instantiation
+  GN_CUDA_CHECK(ensure_smem_optin(optin, out_conv_mma_kernel<H, L256>, (int)smem));
+  out_conv_mma_kernel<H, L256><<<grid, 32 * OM_ROWS, smem, st>>>(static_cast<const H*>(a), static_cast<const uint2*>(wf), bias,
+                                                                out_f32, out_u8, Hh, W, C);
+  return GN_OK;
+}
+
 int launch_out_conv_mma(const void* a, int o16, const void* wf, const float* bias, float* out_f32, uint8_t* out_u8, int B,
                         int H, int W, int C, cudaStream_t st) {
   GN_REQUIRE(o16 != 0 && C % 64 == 0 && C <= 512, "output conv (tensor path): 16-bit operands, C %% 64 == 0, C <= 512");
   const size_t smem = (size_t)9 * (C / 16) * 32 * sizeof(uint2);      // 18 KB for C = 128
   GN_REQUIRE(B <= 65535, "output conv: too many images per pass");
   dim3 grid(ceil_div(W, OM_PIX), ceil_div(H, OM_ROWS), B);
+  // GENIE_B200_OUT_CONV_L256=1: 256-bit activation loads (needs 32-byte aligned pixel rows: C % 16 == 0 holds, base checked)
+  const char* e256 = getenv("GENIE_B200_OUT_CONV_L256");
+  const bool l256 = e256 && e256[0] == '1' && reinterpret_cast<uintptr_t>(a) % 32 == 0;
   if (o16 == 2) {
-    static DevSmemOptIn optin;
-    GN_CUDA_CHECK(ensure_smem_optin(optin, out_conv_mma_kernel<f16>, (int)smem));
-    out_conv_mma_kernel<f16><<<grid, 32 * OM_ROWS, smem, st>>>(static_cast<const f16*>(a), static_cast<const uint2*>(wf), bias,
-                                                              out_f32, out_u8, H, W, C);
+    if (l256) GN_PROPAGATE((launch_om<f16, true>(a, wf, bias, out_f32, out_u8, grid, smem, H, W, C, st)));
+    else GN_PROPAGATE((launch_om<f16, false>(a, wf, bias, out_f32, out_u8, grid, smem, H, W, C, st)));
   } else {
-    static DevSmemOptIn optin;
-    GN_CUDA_CHECK(ensure_smem_optin(optin, out_conv_mma_kernel<bf16>, (int)smem));
-    out_conv_mma_kernel<bf16><<<grid, 32 * OM_ROWS, smem, st>>>(static_cast<const bf16*>(a), static_cast<const uint2*>(wf),
-                                                               bias, out_f32, out_u8, H, W, C);
+    if (l256) GN_PROPAGATE((launch_om<bf16, true>(a, wf, bias, out_f32, out_u8, grid, smem, H, W, C, st)));
+    else GN_PROPAGATE((launch_om<bf16, false>(a, wf, bias, out_f32, out_u8, grid, smem, H, W, C, st)));
   }
   GN_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;
